@@ -1,0 +1,388 @@
+// m1cu_api.cu -- the C ABI of include/m1cu.h: context, sizing, stream-ordered launches and the
+// host-buffer convenience path.  No CPU fallback lives here: every compute entry point needs a
+// CUDA device and reports M1CU_ERR_CUDA otherwise.
+#include "../../include/m1cu.h"
+#include "m1cu_common.cuh"
+#include "m1cu_kernels.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace {
+
+char g_last_error[256] = "";
+
+// Default intra matrix (reference source/image_processing.c:17-26), raster order.
+const int kIntra[64] = {
+     8, 16, 19, 22, 26, 27, 29, 34,   16, 16, 22, 24, 27, 29, 34, 37,
+    19, 22, 26, 27, 29, 34, 34, 38,   22, 22, 26, 27, 29, 34, 37, 40,
+    22, 26, 27, 29, 32, 35, 40, 48,   26, 27, 29, 32, 35, 40, 48, 58,
+    26, 27, 29, 34, 38, 46, 56, 69,   27, 29, 35, 38, 46, 56, 69, 83 };
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct m1cu_ctx {
+    int device = 0;
+    int quality = 0;
+    int max_frames = 0;
+    int batch_frames = 0;           // pictures per launch round (bounds the staging memory)
+    M1Geom g{};
+    M1Quant q{};
+    int32_t qm[64]{};
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    // device state
+    uint32_t *d_staging = nullptr, *d_chunk_bits = nullptr, *d_chunk_dst = nullptr;
+    M1Tables *d_tables = nullptr;
+    int *d_err = nullptr;
+    unsigned long long *d_running = nullptr;
+    unsigned int *d_done = nullptr;
+    // host-path scratch
+    uint8_t *d_in = nullptr;   size_t d_in_cap = 0;
+    uint8_t *d_out = nullptr;  size_t d_out_cap = 0;
+    uint32_t *d_fbytes = nullptr; unsigned long long *d_foff = nullptr; int d_meta_frames = 0;
+    int16_t *d_levels = nullptr; size_t d_levels_cap = 0;
+    uint8_t *h_out = nullptr;  size_t h_out_cap = 0;       // pinned bounce buffer
+    uint32_t *h_fbytes = nullptr; unsigned long long *h_foff = nullptr; int h_meta_frames = 0;
+    unsigned long long launches = 0;
+    char err[256] = "";
+};
+
+namespace {
+
+int fail(m1cu_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
+{
+    char buf[256];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    if (c) memcpy(c->err, buf, sizeof buf);
+    memcpy(g_last_error, buf, sizeof buf);
+    return code;
+}
+
+#define CU(call)                                                              \
+    do {                                                                      \
+        cudaError_t e_ = (call);                                              \
+        if (e_ != cudaSuccess) return fail(ctx, M1CU_ERR_CUDA, #call, e_);    \
+    } while (0)
+
+// (c * mul + ((c >> 31) & mask)) >> shift == c / m (C truncation) for |c| <= 2047 ?
+bool make_quant(const int32_t qm[64], M1Quant *q)
+{
+    for (int k = 0; k < 64; ++k) {
+        const int m = qm[k];
+        if (m < 1 || m > 65535) return false;
+        int fl = 0;
+        while ((2 << fl) <= m) ++fl;                       // floor(log2 m)
+        const int S = 19 + fl;
+        const long long one = 1ll << S;
+        const int K = (int)((one + m - 1) / m);
+        q->mul[k] = K; q->shift[k] = S; q->mask[k] = (int)(one - 1);
+        for (int c = -2047; c <= 2047; ++c) {
+            const long long prod = (long long)c * K + ((c < 0) ? (one - 1) : 0);
+            if (prod > 0x7fffffffll || prod < -0x80000000ll) return false;
+            const int got = (int)(prod >> S);
+            if (got != c / m) return false;
+        }
+    }
+    return true;
+}
+
+int ensure(m1cu_ctx *ctx, void **p, size_t *cap, size_t need, bool pinned = false)
+{
+    if (*cap >= need && *p) return M1CU_OK;
+    if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+    const size_t want = align_up(need + need / 8, 256);
+    CU(pinned ? cudaMallocHost(p, want) : cudaMalloc(p, want));
+    *cap = want;
+    return M1CU_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int m1cu_abi_version(void) { return M1CU_ABI_VERSION; }
+
+int m1cu_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *m1cu_last_error(const m1cu_ctx *ctx) { return ctx ? ctx->err : g_last_error; }
+
+// scale_quantization_matrix, reference source/image_processing.c:314-343: float scale factor,
+// int*float product in float, /100.0 in double, round half away, floor of 1.
+int m1cu_qmatrix(int quality, int32_t out[64])
+{
+    if (!out) return M1CU_ERR_ARG;
+    if (quality < 1) quality = 1;
+    if (quality > 100) quality = 100;
+    const float sf = quality < 50 ? (float)(5000.0 / quality) : (float)(200.0 - 2 * quality);
+    for (int k = 0; k < 64; ++k) {
+        const float prod = (float)kIntra[k] * sf;
+        const int v = (int)round((double)prod / 100.0);
+        out[k] = v < 1 ? 1 : v;
+    }
+    return M1CU_OK;
+}
+
+int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels, int mode,
+                int quality, int max_frames)
+{
+    m1cu_ctx *ctx = nullptr;
+    if (!out) return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: out is NULL");
+    *out = nullptr;
+    if (width <= 0 || height <= 0 || channels < 3 || max_frames <= 0 ||
+        (mode != M1CU_MODE_FULL && mode != M1CU_MODE_REF_COMPAT) || width > 65535 || height > 65535)
+        return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: bad geometry");
+    if (mode == M1CU_MODE_REF_COMPAT) {
+        // the literal loops read columns 0..95, rows 0..143 and chroma offsets up to 71*(W/2)+47
+        if (width < 96 || height < 144 || (size_t)71 * (width / 2) + 47 >= (size_t)width * height)
+            return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: REF_COMPAT needs at least 96x144");
+    }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(nullptr, M1CU_ERR_CUDA, "no CUDA device (this library has no CPU fallback)"); }
+    if (device < 0 || device >= ndev) return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: bad device index");
+
+    ctx = new m1cu_ctx();
+    ctx->device = device; ctx->quality = quality; ctx->max_frames = max_frames;
+    M1Geom &g = ctx->g;
+    g.W = width; g.H = height; g.channels = channels; g.mode = mode;
+    if (mode == M1CU_MODE_FULL) { g.slices = (height + 15) / 16; g.mbs_per_slice = (width + 15) / 16; }
+    else                        { g.slices = 6; g.mbs_per_slice = 9; }
+    g.chunks_per_slice = (g.mbs_per_slice + M1_MAX_CHUNK_MBS - 1) / M1_MAX_CHUNK_MBS;
+    g.chunk_mbs = (g.mbs_per_slice + g.chunks_per_slice - 1) / g.chunks_per_slice;
+    g.chunks_per_slice = (g.mbs_per_slice + g.chunk_mbs - 1) / g.chunk_mbs;
+    g.chunks_per_frame = g.chunks_per_slice * g.slices;
+    g.mbs_per_frame = g.mbs_per_slice * g.slices;
+    g.chunk_stride = (unsigned)align_up(((size_t)M1_SLICE_HDR_BITS + (size_t)g.chunk_mbs * M1_MB_MAX_BITS + 7) / 8 + 8, 16);
+    g.frame_stride = (unsigned long long)width * height * channels;
+
+    m1cu_qmatrix(quality, ctx->qm);
+    if (!make_quant(ctx->qm, &ctx->q)) { delete ctx; return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: quantiser constants failed self-check"); }
+
+#define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(ctx, M1CU_ERR_CUDA, #call, e_); memcpy(g_last_error, ctx->err, sizeof g_last_error); m1cu_destroy(ctx); return rc_; } } while (0)
+    CUC(cudaSetDevice(device));
+    CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+    // bound the staging memory: at most ~1 GiB of chunk records per launch round
+    const size_t per_frame = (size_t)g.chunks_per_frame * g.chunk_stride;
+    size_t batch = ((size_t)1 << 30) / per_frame;
+    if (batch < 1) batch = 1;
+    if (batch > (size_t)max_frames) batch = (size_t)max_frames;
+    ctx->batch_frames = (int)batch;
+    CUC(cudaMalloc(&ctx->d_staging, per_frame * batch));
+    CUC(cudaMalloc(&ctx->d_chunk_bits, sizeof(uint32_t) * g.chunks_per_frame * batch));
+    CUC(cudaMalloc(&ctx->d_chunk_dst, sizeof(uint32_t) * g.chunks_per_frame * batch));
+    CUC(cudaMalloc(&ctx->d_tables, sizeof(M1Tables)));
+    CUC(cudaMalloc(&ctx->d_err, sizeof(int)));
+    CUC(cudaMalloc(&ctx->d_running, sizeof(unsigned long long)));
+    CUC(cudaMalloc(&ctx->d_done, sizeof(unsigned int)));
+    CUC(cudaMemset(ctx->d_err, 0, sizeof(int)));
+    CUC(cudaMemset(ctx->d_done, 0, sizeof(unsigned int)));
+    CUC(cudaMemset(ctx->d_running, 0, sizeof(unsigned long long)));
+    M1Tables ht;
+    m1k_fill_tables(&ht);
+    CUC(cudaMemcpy(ctx->d_tables, &ht, sizeof ht, cudaMemcpyHostToDevice));
+    CUC(m1k_prepare(g));
+#undef CUC
+    *out = ctx;
+    return M1CU_OK;
+}
+
+int m1cu_destroy(m1cu_ctx *ctx)
+{
+    if (!ctx) return M1CU_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->d_staging); cudaFree(ctx->d_chunk_bits); cudaFree(ctx->d_chunk_dst);
+    cudaFree(ctx->d_tables); cudaFree(ctx->d_err); cudaFree(ctx->d_running); cudaFree(ctx->d_done);
+    cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_fbytes); cudaFree(ctx->d_foff);
+    cudaFree(ctx->d_levels);
+    if (ctx->h_out) cudaFreeHost(ctx->h_out);
+    if (ctx->h_fbytes) cudaFreeHost(ctx->h_fbytes);
+    if (ctx->h_foff) cudaFreeHost(ctx->h_foff);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return M1CU_OK;
+}
+
+int m1cu_set_stream(m1cu_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return M1CU_ERR_ARG;
+    if (ctx->own_stream && ctx->stream) { cudaStreamSynchronize(ctx->stream); cudaStreamDestroy(ctx->stream); }
+    ctx->own_stream = false;
+    ctx->stream = (cudaStream_t)cuda_stream;
+    if (!cuda_stream) {
+        CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+    return M1CU_OK;
+}
+
+int m1cu_synchronize(m1cu_ctx *ctx)
+{
+    if (!ctx) return M1CU_ERR_ARG;
+    CU(cudaStreamSynchronize(ctx->stream));
+    return M1CU_OK;
+}
+
+int m1cu_macroblocks_per_frame(const m1cu_ctx *ctx) { return ctx ? ctx->g.mbs_per_frame : 0; }
+size_t m1cu_frame_bytes_in(const m1cu_ctx *ctx) { return ctx ? (size_t)ctx->g.frame_stride : 0; }
+
+size_t m1cu_payload_bound(const m1cu_ctx *ctx)
+{
+    if (!ctx) return 0;
+    const M1Geom &g = ctx->g;
+    const size_t slice_bits = M1_SLICE_HDR_BITS + (size_t)g.mbs_per_slice * M1_MB_MAX_BITS + 7;
+    return align_up((slice_bits / 8) * g.slices, 16);
+}
+
+size_t m1cu_typical_out_bytes(const m1cu_ctx *ctx, int n_frames)
+{
+    if (!ctx || n_frames <= 0) return 0;
+    // a quarter of the coded 4:2:0 sample count per picture: > 10x what natural content needs
+    const size_t per = align_up((size_t)ctx->g.mbs_per_frame * 96 + 256, 16);
+    const size_t bound = m1cu_payload_bound(ctx);
+    return (per < bound ? per : bound) * (size_t)n_frames;
+}
+
+int m1cu_encode_device(m1cu_ctx *ctx, const uint8_t *d_rgb, int n_frames, uint8_t *d_out, size_t out_cap,
+                       uint32_t *d_frame_bytes, uint64_t *d_frame_offsets, int16_t *d_levels)
+{
+    if (!ctx || !d_rgb || !d_out || !d_frame_bytes || !d_frame_offsets || n_frames <= 0)
+        return fail(ctx, M1CU_ERR_ARG, "m1cu_encode_device: bad argument");
+    if (n_frames > ctx->max_frames) return fail(ctx, M1CU_ERR_ARG, "m1cu_encode_device: n_frames > max_frames");
+    if (((uintptr_t)d_out & 15) != 0) return fail(ctx, M1CU_ERR_ARG, "m1cu_encode_device: d_out must be 16-byte aligned");
+    const M1Geom &g = ctx->g;
+    cudaStream_t st = ctx->stream;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemsetAsync(ctx->d_running, 0, sizeof(unsigned long long), st));
+    const int est_words = (int)(g.mbs_per_frame * 24 / 4);
+    int bx = est_words / 1024 + 1;
+    if (bx > 128) bx = 128;
+    for (int f0 = 0; f0 < n_frames; f0 += ctx->batch_frames) {
+        const int nb = n_frames - f0 < ctx->batch_frames ? n_frames - f0 : ctx->batch_frames;
+        CU(m1k_launch_encode(g, ctx->q, d_rgb + (size_t)f0 * g.frame_stride, nb, ctx->d_tables, ctx->d_staging,
+                             ctx->d_chunk_bits, d_levels ? d_levels + (size_t)f0 * g.mbs_per_frame * 384 : nullptr,
+                             ctx->d_err, st));
+        CU(m1k_launch_layout(g, nb, ctx->d_chunk_bits, ctx->d_chunk_dst, d_frame_bytes + f0,
+                             (unsigned long long *)d_frame_offsets + f0, ctx->d_running, ctx->d_done,
+                             (unsigned long long)out_cap, ctx->d_err, st));
+        CU(m1k_launch_stitch(g, nb, bx, ctx->d_staging, ctx->d_chunk_bits, ctx->d_chunk_dst, d_frame_bytes + f0,
+                             (const unsigned long long *)d_frame_offsets + f0, d_out, (unsigned long long)out_cap, st));
+        ctx->launches += 3;
+    }
+    return M1CU_OK;
+}
+
+int m1cu_check(m1cu_ctx *ctx)
+{
+    if (!ctx) return M1CU_ERR_ARG;
+    int flags = 0;
+    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaMemcpy(&flags, ctx->d_err, sizeof flags, cudaMemcpyDeviceToHost));
+    if (flags) CU(cudaMemset(ctx->d_err, 0, sizeof(int)));
+    if (flags & M1_ERRBIT_CAPACITY) return fail(ctx, M1CU_ERR_CAPACITY, "output buffer too small for the encoded payloads");
+    if (flags & M1_ERRBIT_LEVEL) return fail(ctx, M1CU_ERR_LEVEL, "coded AC level with |L| >= 256 (outside the reference's encodable range)");
+    return M1CU_OK;
+}
+
+int m1cu_encode_host(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, uint8_t *h_out, size_t out_cap,
+                     uint32_t *h_frame_bytes, int16_t *h_levels, size_t *total_bytes)
+{
+    if (!ctx || !h_rgb || !h_out || !h_frame_bytes || n_frames <= 0)
+        return fail(ctx, M1CU_ERR_ARG, "m1cu_encode_host: bad argument");
+    if (n_frames > ctx->max_frames) return fail(ctx, M1CU_ERR_ARG, "m1cu_encode_host: n_frames > max_frames");
+    const M1Geom &g = ctx->g;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t in_bytes = (size_t)g.frame_stride * n_frames;
+    int rc;
+    if ((rc = ensure(ctx, (void **)&ctx->d_in, &ctx->d_in_cap, in_bytes))) return rc;
+    if (ctx->d_meta_frames < n_frames) {
+        cudaFree(ctx->d_fbytes); cudaFree(ctx->d_foff); ctx->d_fbytes = nullptr; ctx->d_foff = nullptr;
+        if (ctx->h_fbytes) cudaFreeHost(ctx->h_fbytes);
+        if (ctx->h_foff) cudaFreeHost(ctx->h_foff);
+        ctx->h_fbytes = nullptr; ctx->h_foff = nullptr; ctx->d_meta_frames = 0;
+        CU(cudaMalloc(&ctx->d_fbytes, sizeof(uint32_t) * n_frames));
+        CU(cudaMalloc(&ctx->d_foff, sizeof(unsigned long long) * (n_frames + 1)));
+        CU(cudaMallocHost(&ctx->h_fbytes, sizeof(uint32_t) * n_frames));
+        CU(cudaMallocHost(&ctx->h_foff, sizeof(unsigned long long) * (n_frames + 1)));
+        ctx->d_meta_frames = n_frames;
+    }
+    if (h_levels) {
+        const size_t lb = (size_t)n_frames * g.mbs_per_frame * 384 * sizeof(int16_t);
+        if ((rc = ensure(ctx, (void **)&ctx->d_levels, &ctx->d_levels_cap, lb))) return rc;
+    }
+    CU(cudaMemcpyAsync(ctx->d_in, h_rgb, in_bytes, cudaMemcpyHostToDevice, st));
+
+    size_t want = m1cu_typical_out_bytes(ctx, n_frames);
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((rc = ensure(ctx, (void **)&ctx->d_out, &ctx->d_out_cap, want))) return rc;
+        rc = m1cu_encode_device(ctx, ctx->d_in, n_frames, ctx->d_out, ctx->d_out_cap, ctx->d_fbytes,
+                                (uint64_t *)ctx->d_foff, h_levels ? ctx->d_levels : nullptr);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ctx->h_fbytes, ctx->d_fbytes, sizeof(uint32_t) * n_frames, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->h_foff, ctx->d_foff, sizeof(unsigned long long) * (n_frames + 1), cudaMemcpyDeviceToHost, st));
+        rc = m1cu_check(ctx);
+        if (rc == M1CU_ERR_CAPACITY && attempt == 0) { want = m1cu_payload_bound(ctx) * (size_t)n_frames; continue; }
+        if (rc) return rc;
+        break;
+    }
+    const size_t dev_bytes = (size_t)ctx->h_foff[n_frames];
+    if ((rc = ensure(ctx, (void **)&ctx->h_out, &ctx->h_out_cap, dev_bytes ? dev_bytes : 16, true))) return rc;
+    CU(cudaMemcpyAsync(ctx->h_out, ctx->d_out, dev_bytes, cudaMemcpyDeviceToHost, st));
+    if (h_levels)
+        CU(cudaMemcpyAsync(h_levels, ctx->d_levels, (size_t)n_frames * g.mbs_per_frame * 384 * sizeof(int16_t),
+                           cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    size_t pos = 0;
+    for (int f = 0; f < n_frames; ++f) {
+        const size_t n = ctx->h_fbytes[f];
+        if (pos + n > out_cap) return fail(ctx, M1CU_ERR_CAPACITY, "m1cu_encode_host: h_out too small");
+        memcpy(h_out + pos, ctx->h_out + ctx->h_foff[f], n);
+        h_frame_bytes[f] = (uint32_t)n;
+        pos += n;
+    }
+    if (total_bytes) *total_bytes = pos;
+    return M1CU_OK;
+}
+
+int m1cu_ycbcr_planes(m1cu_ctx *ctx, const uint8_t *d_rgb, uint8_t *d_y, uint8_t *d_cb, uint8_t *d_cr)
+{
+    if (!ctx || !d_rgb || !d_y || !d_cb || !d_cr) return fail(ctx, M1CU_ERR_ARG, "m1cu_ycbcr_planes: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(m1k_launch_planes(d_rgb, ctx->g.channels, (size_t)ctx->g.W * ctx->g.H, d_y, d_cb, d_cr, ctx->stream));
+    ctx->launches += 1;
+    return M1CU_OK;
+}
+
+int m1cu_synth_rgb(m1cu_ctx *ctx, uint32_t seed, long first_frame, int n_frames, int kind, uint8_t *d_rgb)
+{
+    if (!ctx || !d_rgb || n_frames <= 0 || ctx->g.channels != 3)
+        return fail(ctx, M1CU_ERR_ARG, "m1cu_synth_rgb: bad argument (needs a 3-channel context)");
+    CU(cudaSetDevice(ctx->device));
+    CU(m1k_launch_synth(seed, first_frame, n_frames, ctx->g.W, ctx->g.H, kind, d_rgb, ctx->stream));
+    ctx->launches += 1;
+    return M1CU_OK;
+}
+
+unsigned long long m1cu_launch_count(const m1cu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void *m1cu_device_alloc(size_t bytes) { void *p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+void  m1cu_device_free(void *p) { if (p) cudaFree(p); }
+void *m1cu_pinned_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
+void  m1cu_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+int   m1cu_memcpy_h2d(void *dst, const void *src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? M1CU_OK : M1CU_ERR_CUDA; }
+int   m1cu_memcpy_d2h(void *dst, const void *src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? M1CU_OK : M1CU_ERR_CUDA; }
+
+}  // extern "C"

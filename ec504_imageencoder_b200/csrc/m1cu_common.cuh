@@ -1,0 +1,50 @@
+// m1cu_common.cuh -- shared declarations for the sm_100a MPEG-1 I-frame path.
+//
+// Pipeline (one launch sequence per batch of pictures):
+//   k_encode_chunks   RGB -> exact YCbCr -> 4:2:0 -> 8x8 int32 DCT -> quantise -> zigzag ->
+//                     DC/AC VLC -> bits of one "chunk" (<= chunk_mbs macroblocks of one slice)
+//                     packed MSB-first in shared memory -> chunk staging + chunk bit count
+//   k_layout          per picture: slice/chunk bit offsets (slices byte-aligned), picture sizes,
+//                     then (last CTA) 16-byte-aligned picture offsets
+//   k_stitch          funnel-shifts the chunk bit strings into the final payload bytes
+//
+// Reference behaviour reproduced (paths relative to the reference checkout): see include/m1cu.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define M1_MAX_CHUNK_MBS 40          // macroblocks per chunk (240 block-threads)
+#define M1_BLOCK_MAX_BITS 901
+#define M1_MB_MAX_BITS (2 + 6 * M1_BLOCK_MAX_BITS)
+#define M1_SLICE_HDR_BITS 38
+#define M1_WIN_WORDS 1024            // shared-memory bit window per chunk pass (4 KiB = 32768 bits)
+
+enum { M1_ERRBIT_CAPACITY = 1, M1_ERRBIT_LEVEL = 2 };
+
+struct M1Geom {
+    int W, H, channels;
+    int mode;                  // M1CU_MODE_*
+    int slices;                // per picture
+    int mbs_per_slice;
+    int chunk_mbs;             // macroblocks per chunk (last chunk of a slice may hold fewer)
+    int chunks_per_slice;
+    int chunks_per_frame;
+    int mbs_per_frame;
+    unsigned chunk_stride;     // staging bytes per chunk (multiple of 16)
+    unsigned long long frame_stride;   // input bytes per picture
+};
+
+// Quantiser constants for raster position k: level = (c * mul + ((c >> 31) & mask)) >> shift
+// == C truncating division c / m (source/image_processing.c:367) for |c| <= 2047; checked
+// exhaustively on the host when the context is created.
+struct M1Quant {
+    int mul[64];
+    int mask[64];
+    int shift[64];
+};
+
+struct M1Tables {
+    uint32_t ac[112];
+    uint32_t dc[18];
+    uint8_t  first[36];
+};

@@ -1,0 +1,652 @@
+// m1cu_kernels.cu -- hand-written sm_100a kernels for the MPEG-1 I-frame per-block path.
+// See m1cu_common.cuh for the pipeline and include/m1cu.h for the reference interfaces replaced.
+#include "m1cu_common.cuh"
+#include "m1cu_kernels.h"
+#include "m1cu_tables.h"
+
+// -------------------------------------------------------------------------------------------
+// Exact colour conversion.  The reference (source/image_processing.c:104-106) evaluates
+//   Y  = (uchar)(0.299 r + 0.587 g + 0.114 b)
+//   Cb = (uchar)(128 - 0.168736 r - 0.331264 g + 0.5 b)
+//   Cr = (uchar)(128 + 0.5 r - 0.418688 g - 0.081312 b)
+// in IEEE double, left to right, products rounded separately (gcc -O0, SSE2, no FMA), then
+// truncates.  __dmul_rn/__dadd_rn/__dsub_rn are never contracted into FMAs, so this is the same
+// arithmetic bit for bit.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ycbcr_exact(int r, int g, int b, int &y, int &cb, int &cr)
+{
+    const double rd = __int2double_rn(r), gd = __int2double_rn(g), bd = __int2double_rn(b);
+    double t = __dadd_rn(__dmul_rn(0.299, rd), __dmul_rn(0.587, gd));
+    t = __dadd_rn(t, __dmul_rn(0.114, bd));
+    y = __double2int_rz(t);
+    double u = __dsub_rn(128.0, __dmul_rn(0.168736, rd));
+    u = __dsub_rn(u, __dmul_rn(0.331264, gd));
+    u = __dadd_rn(u, __dmul_rn(0.5, bd));
+    cb = __double2int_rz(u);
+    double v = __dadd_rn(128.0, __dmul_rn(0.5, rd));
+    v = __dsub_rn(v, __dmul_rn(0.418688, gd));
+    v = __dsub_rn(v, __dmul_rn(0.081312, bd));
+    cr = __double2int_rz(v);
+}
+
+// -------------------------------------------------------------------------------------------
+// 8-point integer butterfly of fast_DCT (source/image_processing.c:210-238).  On return
+//   t0 = k0 sum, t1 = k4 diff, t2 = k2 (unshifted), t3 = k6 (unshifted),
+//   t4/t5: k1 = t4 + t5, k7 = t4 - t5 (unshifted), t6 -> k3, t7 -> k5 (before the r2 scaling).
+// -------------------------------------------------------------------------------------------
+struct Fdct8 { int t0, t1, t2, t3, t4, t5, t6, t7; };
+
+__device__ __forceinline__ Fdct8 fdct_core(int x0, int x1, int x2, int x3, int x4, int x5, int x6, int x7)
+{
+    const int c1 = 1004, s1 = 200, c3 = 851, s3 = 569, r2c6 = 554, r2s6 = 1337;
+    const int a0 = x0 + x7, d0 = x0 - x7;
+    const int a1 = x1 + x6, d1 = x1 - x6;
+    const int a2 = x2 + x5, d2 = x2 - x5;
+    const int a3 = x3 + x4, d3 = x3 - x4;
+    const int e0 = a0 + a3, e3 = a0 - a3;
+    const int e1 = a1 + a2, e2 = a1 - a2;
+    const int m12 = c1 * (d1 + d2);
+    const int p2 = (-s1 - c1) * d2 + m12;
+    const int p1 = (s1 - c1) * d1 + m12;
+    const int m03 = c3 * (d0 + d3);
+    const int p3 = (-s3 - c3) * d3 + m03;
+    const int p0 = (s3 - c3) * d0 + m03;
+    const int m78 = r2c6 * (e2 + e3);
+    Fdct8 o;
+    o.t0 = e0 + e1;
+    o.t1 = e0 - e1;
+    o.t2 = (r2s6 - r2c6) * e3 + m78;
+    o.t3 = (-r2s6 - r2c6) * e2 + m78;
+    o.t5 = p0 + p2;
+    o.t7 = p0 - p2;
+    o.t4 = p3 + p1;
+    o.t6 = p3 - p1;
+    return o;
+}
+
+// Forward DCT of one 8x8 block held in registers: v[i*8+j] in, dct[u*8+v] out (in place).
+// Row pass source/image_processing.c:198-250, column pass :253-305.
+__device__ __forceinline__ void fdct8x8(int (&v)[64])
+{
+    const int r2 = 181;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        Fdct8 o = fdct_core(v[i * 8 + 0], v[i * 8 + 1], v[i * 8 + 2], v[i * 8 + 3],
+                            v[i * 8 + 4], v[i * 8 + 5], v[i * 8 + 6], v[i * 8 + 7]);
+        v[i * 8 + 0] = o.t0;
+        v[i * 8 + 4] = o.t1;
+        v[i * 8 + 2] = o.t2 >> 10;
+        v[i * 8 + 6] = o.t3 >> 10;
+        v[i * 8 + 7] = (o.t4 - o.t5) >> 10;
+        v[i * 8 + 1] = (o.t4 + o.t5) >> 10;
+        v[i * 8 + 3] = (o.t6 * r2) >> 17;
+        v[i * 8 + 5] = (o.t7 * r2) >> 17;
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        Fdct8 o = fdct_core(v[0 * 8 + j], v[1 * 8 + j], v[2 * 8 + j], v[3 * 8 + j],
+                            v[4 * 8 + j], v[5 * 8 + j], v[6 * 8 + j], v[7 * 8 + j]);
+        v[0 * 8 + j] = (o.t0 + 16) >> 3;
+        v[4 * 8 + j] = (o.t1 + 16) >> 3;
+        v[2 * 8 + j] = (o.t2 + 16384) >> 13;
+        v[6 * 8 + j] = (o.t3 + 16384) >> 13;
+        v[7 * 8 + j] = (o.t4 - o.t5 + 16384) >> 13;
+        v[1 * 8 + j] = (o.t4 + o.t5 + 16384) >> 13;
+        v[3 * 8 + j] = ((o.t6 >> 8) * r2 + 8192) >> 12;
+        v[5 * 8 + j] = ((o.t7 >> 8) * r2 + 8192) >> 12;
+    }
+}
+
+// zigzag rank of raster position k (source/image_processing.c:28-37), compile-time table
+__host__ __device__ constexpr int zz_rank(int k)
+{
+    constexpr int t[64] = { 0,  1,  5,  6, 14, 15, 27, 28,  2,  4,  7, 13, 16, 26, 29, 42,
+                            3,  8, 12, 17, 25, 30, 41, 43,  9, 11, 18, 24, 31, 40, 44, 53,
+                           10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60,
+                           21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63 };
+    return t[k];
+}
+__host__ __device__ constexpr int zz_raster(int z)
+{
+    for (int k = 0; k < 64; ++k) if (zz_rank(k) == z) return k;
+    return 0;
+}
+
+// -------------------------------------------------------------------------------------------
+// Bit sinks for the block coder.
+// -------------------------------------------------------------------------------------------
+struct BitCounter {
+    int n;
+    __device__ __forceinline__ void put(uint32_t, int len) { n += len; }
+};
+
+// Writes MSB-first into a shared-memory window of logical 32-bit words covering stream bits
+// [w0, w0 + 32*M1_WIN_WORDS); bits outside the window are dropped (another pass takes them).
+struct WindowWriter {
+    uint32_t *win;
+    int pos;   // absolute bit position in the chunk
+    int w0;
+    __device__ __forceinline__ void put(uint32_t code, int len)
+    {
+        const int p = pos - w0;
+        pos += len;
+        if (p + len <= 0 || p >= 32 * M1_WIN_WORDS) return;
+        const int word = p >> 5, o = p & 31;
+        const unsigned long long sh = ((unsigned long long)code << (64 - len)) >> o;
+        const uint32_t hi = (uint32_t)(sh >> 32), lo = (uint32_t)sh;
+        if (hi && word >= 0 && word < M1_WIN_WORDS) atomicOr(&win[word], hi);
+        if (lo && word + 1 >= 0 && word + 1 < M1_WIN_WORDS) atomicOr(&win[word + 1], lo);
+    }
+};
+
+// 16-byte-chunk XOR swizzle of a thread's 128-byte level record (conflict-free 128-bit stores)
+__device__ __forceinline__ int lvl_index(int tid, int z)
+{
+    return tid * 64 + ((((z >> 3) ^ tid) & 7) << 3) + (z & 7);
+}
+
+// One block's bits: DC (source/mpeg1_blk.c:67-113), AC walk (source/image_processing.c:400-433,
+// source/vlc.c:315-385), end of block (source/mpeg1_blk.c:115-117).  lv: this thread's zigzag
+// levels in shared memory; nz: bit z set <=> level z non-zero.  Returns non-zero when a coded AC
+// level is outside the reference's encodable range.
+template <class Sink>
+__device__ __forceinline__ int code_block(Sink &s, const short *lv_base, int tid, unsigned long long nz,
+                                          bool is_luma, const M1Tables *tb)
+{
+    int bad = 0;
+    int prev = -1;
+    unsigned long long m = nz;
+    if (nz & 1ull) {
+        const int v = lv_base[lvl_index(tid, 0)];
+        int c = v < 0 ? -v : v;
+        const int low = c & 0xff;
+        const int sz = low ? 32 - __clz(low) : 1;            // highest set bit of bits 0..7, default 1
+        const uint32_t e = tb->dc[sz + (is_luma ? 0 : 9)];
+        if (v < 0) c ^= 1 << (sz - 1);
+        const uint32_t val = (uint32_t)c & ((1u << sz) - 1u);
+        s.put(((e & 0xffffffu) << sz) | val, (int)(e >> 24) + sz);
+        prev = 0;
+        m &= ~1ull;
+    } else {
+        if (is_luma) s.put(4u, 3); else s.put(0u, 2);
+    }
+    // coding stops at the first non-zero whose predecessor position is also non-zero
+    const unsigned long long adj = nz & (nz << 1);
+    if (adj) m &= (adj & (0ull - adj)) - 1ull;
+    while (m) {
+        const int k = __ffsll((long long)m) - 1;
+        m &= m - 1ull;
+        const int L = lv_base[lvl_index(tid, k)];
+        const int r = k - prev - 2;                          // run - 1 of source/vlc.c:326
+        const int mag = L < 0 ? -L : L;
+        const int a = mag - 1;
+        prev = k;
+        if (r == 0 && a == 0) { s.put(3u, 2); continue; }
+        if (r <= 31) {
+            const int f = tb->first[r];
+            if (a < (int)tb->first[r + 1] - f) {
+                const uint32_t e = tb->ac[f + a];
+                s.put(e & 0xffffffu, (int)(e >> 24));
+                continue;
+            }
+        }
+        if (mag >= 256) bad = 1;                             // reference: NULL -> crash
+        const uint32_t head = (1u << 6) | (uint32_t)(r & 0x3f);    // 000001 rrrrrr
+        if (mag < 128) s.put((head << 8) | ((uint32_t)L & 0xffu), 20);
+        else           s.put((head << 16) | (L < 0 ? 0x8000u : 0u) | ((uint32_t)L & 0xffu), 28);
+    }
+    s.put(2u, 2);
+    return bad;
+}
+
+// -------------------------------------------------------------------------------------------
+// k_encode_chunks: one CTA per (chunk, slice, picture).
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ const uint8_t *px_ptr(const uint8_t *frame, const M1Geom &g, int x, int y)
+{
+    x = min(x, g.W - 1);
+    y = min(y, g.H - 1);
+    return frame + ((size_t)y * g.W + x) * g.channels;
+}
+
+template <bool kLevels>
+__global__ void __launch_bounds__(256)
+k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quant q,
+                const uint8_t *__restrict__ rgb, const M1Tables *__restrict__ gtab,
+                uint32_t *__restrict__ staging, uint32_t *__restrict__ chunk_bits,
+                short *__restrict__ levels, int *__restrict__ err)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const int chunk = blockIdx.x, slice = blockIdx.y, frame = blockIdx.z;
+    const int mb0 = chunk * g.chunk_mbs;
+    const int nmb = min(g.chunk_mbs, g.mbs_per_slice - mb0);
+    const int ypitch = 16 * g.chunk_mbs, cpitch = 8 * g.chunk_mbs;
+
+    // shared memory carve-up
+    uint8_t *Ys  = smem;                                   // [16][ypitch]
+    uint8_t *Cbs = Ys + 16 * ypitch;                       // [8][cpitch]
+    uint8_t *Crs = Cbs + 8 * cpitch;                       // [8][cpitch]
+    short   *lvl = (short *)(Crs + 8 * cpitch);            // [nthr][64] swizzled
+    uint32_t *win = (uint32_t *)(lvl + (size_t)nthr * 64); // [M1_WIN_WORDS]
+    M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS);
+    int *scan = (int *)(tb + 1);                           // [32] warp totals + [1] chunk total
+
+    for (int i = tid; i < (int)(sizeof(M1Tables) / 4); i += nthr) ((uint32_t *)tb)[i] = ((const uint32_t *)gtab)[i];
+
+    const uint8_t *fr = rgb + (size_t)frame * g.frame_stride;
+
+    // ---- phase 1: colour conversion into the chunk's planes --------------------------------
+    if (g.mode == 0) {
+        // FULL: slice = macroblock row; chunk covers columns [16*mb0, 16*(mb0+nmb)); chroma is the
+        // truncating mean of each 2x2 (source/image_processing.c:126-130); coordinates are
+        // clamped = edge replication up to the coded size.
+        const int qw = 8 * nmb;
+        for (int qi = tid; qi < 8 * qw; qi += nthr) {
+            const int qy = qi / qw, qx = qi - qy * qw;
+            const int x = 16 * mb0 + 2 * qx, y = 16 * slice + 2 * qy;
+            int sb = 0, sr = 0;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const uint8_t *p = px_ptr(fr, g, x + dx, y + dy);
+                    int yy, cb, cr;
+                    ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
+                    Ys[(2 * qy + dy) * ypitch + 2 * qx + dx] = (uint8_t)yy;
+                    sb += cb; sr += cr;
+                }
+            Cbs[qy * cpitch + qx] = (uint8_t)(sb >> 2);
+            Crs[qy * cpitch + qx] = (uint8_t)(sr >> 2);
+        }
+    } else {
+        // REF_COMPAT (include/encoder.h:238-348): "slice" s is the 16-pixel column x = 16*s, the
+        // macroblocks walk down rows y = 16*mb; chroma blocks are 8 consecutive bytes of the
+        // FULL-resolution planes at linear offset (y/2+i)*(W/2) + x/2 + j.
+        const int x0 = 16 * slice;
+        for (int i = tid; i < 256 * nmb; i += nthr) {
+            const int mb = i >> 8, r = (i >> 4) & 15, c = i & 15;
+            const uint8_t *p = fr + ((size_t)(16 * (mb0 + mb) + r) * g.W + x0 + c) * g.channels;
+            int yy, cb, cr;
+            ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
+            Ys[r * ypitch + 16 * mb + c] = (uint8_t)yy;
+        }
+        const int half = g.W / 2;
+        for (int i = tid; i < 64 * nmb; i += nthr) {
+            const int mb = i >> 6, r = (i >> 3) & 7, c = i & 7;
+            const size_t off = (size_t)(8 * (mb0 + mb) + r) * half + x0 / 2 + c;
+            const uint8_t *p = fr + off * g.channels;      // pixel `off` of the row-major picture
+            int yy, cb, cr;
+            ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
+            Cbs[r * cpitch + 8 * mb + c] = (uint8_t)cb;
+            Crs[r * cpitch + 8 * mb + c] = (uint8_t)cr;
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: one thread per 8x8 block: DCT, quantise, zigzag ---------------------------
+    const int mb = tid / 6, blk = tid - mb * 6;
+    const bool active = mb < nmb;
+    const bool is_luma = blk < 4;
+    unsigned long long nz = 0;
+    if (active) {
+        int v[64];
+        const uint8_t *src; int pitch;
+        if (is_luma) { src = Ys + ((blk >> 1) * 8) * ypitch + 16 * mb + (blk & 1) * 8; pitch = ypitch; }
+        else         { src = (blk == 4 ? Cbs : Crs) + 8 * mb; pitch = cpitch; }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const uint2 w = *(const uint2 *)(src + i * pitch);
+            v[i * 8 + 0] = w.x & 0xff; v[i * 8 + 1] = (w.x >> 8) & 0xff;
+            v[i * 8 + 2] = (w.x >> 16) & 0xff; v[i * 8 + 3] = w.x >> 24;
+            v[i * 8 + 4] = w.y & 0xff; v[i * 8 + 5] = (w.y >> 8) & 0xff;
+            v[i * 8 + 6] = (w.y >> 16) & 0xff; v[i * 8 + 7] = w.y >> 24;
+        }
+        fdct8x8(v);
+        // quantise: truncating division by the scaled matrix (source/image_processing.c:367)
+#pragma unroll
+        for (int k = 0; k < 64; ++k) {
+            const int c = v[k];
+            v[k] = (c * q.mul[k] + ((c >> 31) & q.mask[k])) >> q.shift[k];
+        }
+        // zigzag (source/image_processing.c:373-381) + pack to int16 + non-zero mask
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int z = 0; z < 32; ++z) if (v[zz_raster(z)] != 0) lo |= 1u << z;
+#pragma unroll
+        for (int z = 32; z < 64; ++z) if (v[zz_raster(z)] != 0) hi |= 1u << (z - 32);
+        nz = ((unsigned long long)hi << 32) | lo;
+#pragma unroll
+        for (int cidx = 0; cidx < 8; ++cidx) {
+            uint4 w;
+            w.x = (uint32_t)(v[zz_raster(cidx * 8 + 0)] & 0xffff) | ((uint32_t)v[zz_raster(cidx * 8 + 1)] << 16);
+            w.y = (uint32_t)(v[zz_raster(cidx * 8 + 2)] & 0xffff) | ((uint32_t)v[zz_raster(cidx * 8 + 3)] << 16);
+            w.z = (uint32_t)(v[zz_raster(cidx * 8 + 4)] & 0xffff) | ((uint32_t)v[zz_raster(cidx * 8 + 5)] << 16);
+            w.w = (uint32_t)(v[zz_raster(cidx * 8 + 6)] & 0xffff) | ((uint32_t)v[zz_raster(cidx * 8 + 7)] << 16);
+            *(uint4 *)(lvl + tid * 64 + (((cidx ^ tid) & 7) << 3)) = w;
+        }
+    }
+    __syncthreads();
+
+    if (kLevels) {
+        // debug output: zigzag levels in coding order, [picture][macroblock][6][64]
+        short *dst = levels + ((size_t)frame * g.mbs_per_frame + (size_t)slice * g.mbs_per_slice + mb0) * 384;
+        for (int i = tid; i < nmb * 384; i += nthr) {
+            const int t = i >> 6, z = i & 63;
+            dst[i] = lvl[lvl_index(t, z)];
+        }
+    }
+
+    // ---- phase 3: bit lengths, offsets, packing ----------------------------------------------
+    const bool slice_head = active && tid == 0 && chunk == 0;
+    int my_bits = 0, bad = 0;
+    if (active) {
+        BitCounter bc{0};
+        bad = code_block(bc, lvl, tid, nz, is_luma, tb);
+        my_bits = bc.n + (blk == 0 ? 2 : 0) + (slice_head ? M1_SLICE_HDR_BITS : 0);
+    }
+    if (bad) atomicOr(err, M1_ERRBIT_LEVEL);
+
+    // block-wide exclusive scan of my_bits
+    const int lane = tid & 31, warp = tid >> 5;
+    int incl = my_bits;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    if (lane == 31) scan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = (nthr + 31) >> 5;
+        int w = lane < nw ? scan[lane] : 0;
+        int wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, wi, d);
+            if (lane >= d) wi += t;
+        }
+        if (lane < nw) scan[lane] = wi - w;
+        if (lane == 31) scan[32] = wi;
+    }
+    __syncthreads();
+    const int my_off = scan[warp] + incl - my_bits;
+    const int total_bits = scan[32];
+
+    uint32_t *out = staging + ((size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk)
+                                  * (g.chunk_stride / 4);
+    for (int w0 = 0; w0 < total_bits; w0 += 32 * M1_WIN_WORDS) {
+        for (int i = tid; i < M1_WIN_WORDS; i += nthr) win[i] = 0;
+        __syncthreads();
+        if (active && my_off < w0 + 32 * M1_WIN_WORDS && my_off + my_bits > w0) {
+            WindowWriter ww{win, my_off, w0};
+            if (slice_head) {
+                // source/mpeg1_blk.c:12-20: 000001 | (vertical_pos+1)&0xff | quant_scale(5)=1 | 0
+                ww.put(1u, 24);
+                ww.put(((((uint32_t)(slice & 0xff) + 1u) & 0xffu) << 6) | (1u << 1), 14);
+            }
+            if (blk == 0) ww.put(3u, 2);   // address increment '1' + macroblock_type '1'
+            code_block(ww, lvl, tid, nz, is_luma, tb);
+        }
+        __syncthreads();
+        const int nwords = min(M1_WIN_WORDS, (total_bits - w0 + 31) >> 5);
+        for (int i = tid; i < nwords; i += nthr) out[(w0 >> 5) + i] = win[i];
+        __syncthreads();
+    }
+    if (tid == 0)
+        chunk_bits[(size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk] = (uint32_t)total_bits;
+}
+
+// -------------------------------------------------------------------------------------------
+// k_layout: one CTA per picture.  Slice s starts at a byte boundary (include/encoder.h:442-443);
+// chunk c of slice s starts at slice start + bits of the slice's earlier chunks.  The last CTA
+// to finish turns the picture sizes into 16-byte-aligned offsets, continuing from *running.
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_layout(const __grid_constant__ M1Geom g, int n_frames, const uint32_t *__restrict__ chunk_bits,
+         uint32_t *__restrict__ chunk_dst, uint32_t *__restrict__ frame_bytes,
+         unsigned long long *__restrict__ frame_off, unsigned long long *running,
+         unsigned int *done_counter, unsigned long long out_cap, int *err)
+{
+    __shared__ unsigned int wsum[8];
+    __shared__ unsigned int carry;
+    __shared__ bool is_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int f = blockIdx.x;
+    const uint32_t *cb = chunk_bits + (size_t)f * g.chunks_per_frame;
+    uint32_t *cd = chunk_dst + (size_t)f * g.chunks_per_frame;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int s0 = 0; s0 < g.slices; s0 += 256) {
+        const int s = s0 + tid;
+        unsigned int bits = 0;
+        if (s < g.slices) {
+            for (int c = 0; c < g.chunks_per_slice; ++c) bits += cb[s * g.chunks_per_slice + c];
+            bits = (bits + 7u) & ~7u;
+        }
+        unsigned int incl = bits;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned int base = carry;
+        for (int w = 0; w < warp; ++w) base += wsum[w];
+        if (s < g.slices) {
+            unsigned int pos = base + incl - bits;
+            for (int c = 0; c < g.chunks_per_slice; ++c) {
+                cd[s * g.chunks_per_slice + c] = pos;
+                pos += cb[s * g.chunks_per_slice + c];
+            }
+        }
+        __syncthreads();
+        if (tid == 255) carry = base + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        frame_bytes[f] = carry >> 3;
+        __threadfence();
+        const unsigned int prev = atomicAdd(done_counter, 1u);
+        is_last = (prev == (unsigned int)n_frames - 1u);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // serial-by-tile exclusive scan of the aligned picture sizes (n_frames is small)
+    if (warp == 0) {
+        unsigned long long base = *running;
+        for (int f0 = 0; f0 < n_frames; f0 += 32) {
+            const int ff = f0 + lane;
+            const unsigned long long sz = ff < n_frames ? (((unsigned long long)((volatile uint32_t *)frame_bytes)[ff] + 15ull) & ~15ull) : 0ull;
+            unsigned long long incl = sz;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+                if (lane >= d) incl += t;
+            }
+            if (ff < n_frames) frame_off[ff] = base + incl - sz;
+            base += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) {
+            frame_off[n_frames] = base;
+            *running = base;
+            *done_counter = 0;
+            if (base > out_cap) atomicOr(err, M1_ERRBIT_CAPACITY);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// k_stitch: every thread produces 32-bit words of the final payload.  blockIdx.y = picture.
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t read_bits(const uint32_t *__restrict__ src, unsigned int bit, int n)
+{
+    // n in 1..32 bits starting at `bit` of a logical MSB-first word array
+    const unsigned int w = bit >> 5, o = bit & 31;
+    unsigned long long v = (unsigned long long)src[w] << 32;
+    if (o + n > 32) v |= src[w + 1];
+    return (uint32_t)((v << o) >> (64 - n));
+}
+
+__global__ void __launch_bounds__(256)
+k_stitch(const __grid_constant__ M1Geom g, const uint32_t *__restrict__ staging,
+         const uint32_t *__restrict__ chunk_bits, const uint32_t *__restrict__ chunk_dst,
+         const uint32_t *__restrict__ frame_bytes, const unsigned long long *__restrict__ frame_off,
+         uint8_t *__restrict__ out, unsigned long long out_cap)
+{
+    const int f = blockIdx.y;
+    const unsigned int fbytes = frame_bytes[f];
+    const unsigned long long foff = frame_off[f];
+    if (foff + ((fbytes + 15ull) & ~15ull) > out_cap) return;      // flagged by k_layout
+    const unsigned int nwords = (fbytes + 3u) >> 2;
+    const uint32_t *cb = chunk_bits + (size_t)f * g.chunks_per_frame;
+    const uint32_t *cd = chunk_dst + (size_t)f * g.chunks_per_frame;
+    const int nc = g.chunks_per_frame;
+    uint32_t *dst = (uint32_t *)(out + foff);
+    for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
+        unsigned int b = w * 32u;
+        const unsigned int end = b + 32u;
+        // largest c with cd[c] <= b
+        int lo = 0, hi = nc - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (cd[mid] <= b) lo = mid; else hi = mid - 1;
+        }
+        int c = lo;
+        uint32_t acc = 0;
+        while (b < end && c < nc) {
+            const unsigned int cs = cd[c], ce = cs + cb[c];
+            if (b < ce) {
+                const int take = (int)(min(end, ce) - b);
+                const uint32_t *src = staging + (size_t)((size_t)f * nc + c) * (g.chunk_stride / 4);
+                const uint32_t bits = read_bits(src, b - cs, take);
+                acc |= bits << (end - b - take);
+                b += take;
+            }
+            if (b >= ce) {
+                ++c;
+                if (c < nc) { const unsigned int ns = cd[c]; if (ns > b) b = min(end, ns); }  // slice padding zeros
+                else b = end;
+            }
+        }
+        dst[w] = __byte_perm(acc, 0, 0x0123);
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Full-resolution planes (the .bit side files, source/image_processing.c:753-787) and the
+// synthetic generator (same integer formula as oracle/m1_oracle.c:m1o_synth_rgb).
+// -------------------------------------------------------------------------------------------
+__global__ void k_ycbcr_planes(const uint8_t *__restrict__ rgb, int channels, size_t npix,
+                               uint8_t *__restrict__ Y, uint8_t *__restrict__ Cb, uint8_t *__restrict__ Cr)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
+        const uint8_t *p = rgb + i * channels;
+        int y, cb, cr;
+        ycbcr_exact(p[0], p[1], p[2], y, cb, cr);
+        Y[i] = (uint8_t)y; Cb[i] = (uint8_t)cb; Cr[i] = (uint8_t)cr;
+    }
+}
+
+__device__ __forceinline__ uint32_t mix32(uint32_t x)
+{
+    x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
+    return x;
+}
+
+__global__ void k_synth_rgb(uint32_t seed, long first_frame, int n_frames, int W, int H, int kind,
+                            uint8_t *__restrict__ rgb)
+{
+    const size_t per = (size_t)W * H;
+    const size_t total = per * n_frames;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t fi = i / per, p = i - fi * per;
+        const uint32_t f = (uint32_t)(first_frame + (long)fi);
+        const uint32_t y = (uint32_t)(p / W), x = (uint32_t)(p - (size_t)y * W);
+        const uint32_t fkey = mix32(seed * 0x85ebca6bu + f * 0x9e3779b9u + 0x165667b1u);
+        const uint32_t n = mix32(fkey ^ (y * (uint32_t)W + x));
+        uint8_t *o = rgb + i * 3;
+        if (kind == 1) {
+            o[0] = (uint8_t)n; o[1] = (uint8_t)(n >> 8); o[2] = (uint8_t)(n >> 16);
+        } else {
+            o[0] = (uint8_t)((255u * x / (uint32_t)W + (n & 15u) + f) & 255u);
+            o[1] = (uint8_t)((255u * y / (uint32_t)H + ((n >> 4) & 15u)) & 255u);
+            o[2] = (uint8_t)(((x + y) / 8u + ((n >> 8) & 15u) + 2u * f) & 255u);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// Launchers (called from m1cu_api.cu).
+// -------------------------------------------------------------------------------------------
+size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
+{
+    return (size_t)16 * 16 * g.chunk_mbs + 2 * (size_t)8 * 8 * g.chunk_mbs + (size_t)threads * 128
+           + (size_t)M1_WIN_WORDS * 4 + sizeof(M1Tables) + 33 * sizeof(int) + 16;
+}
+
+int m1k_encode_threads(const M1Geom &g) { return (6 * g.chunk_mbs + 31) & ~31; }
+
+cudaError_t m1k_prepare(const M1Geom &g)
+{
+    const size_t smem = m1k_encode_smem_bytes(g, m1k_encode_threads(g));
+    cudaError_t e = cudaFuncSetAttribute(k_encode_chunks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_encode_chunks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+cudaError_t m1k_launch_encode(const M1Geom &g, const M1Quant &q, const uint8_t *rgb, int n_frames,
+                              const M1Tables *tables, uint32_t *staging, uint32_t *chunk_bits,
+                              short *levels, int *err, cudaStream_t st)
+{
+    const int threads = m1k_encode_threads(g);
+    const size_t smem = m1k_encode_smem_bytes(g, threads);
+    dim3 grid(g.chunks_per_slice, g.slices, n_frames);
+    if (levels) k_encode_chunks<true><<<grid, threads, smem, st>>>(g, q, rgb, tables, staging, chunk_bits, levels, err);
+    else        k_encode_chunks<false><<<grid, threads, smem, st>>>(g, q, rgb, tables, staging, chunk_bits, levels, err);
+    return cudaGetLastError();
+}
+
+cudaError_t m1k_launch_layout(const M1Geom &g, int n_frames, const uint32_t *chunk_bits, uint32_t *chunk_dst,
+                              uint32_t *frame_bytes, unsigned long long *frame_off,
+                              unsigned long long *running, unsigned int *done_counter,
+                              unsigned long long out_cap, int *err, cudaStream_t st)
+{
+    k_layout<<<n_frames, 256, 0, st>>>(g, n_frames, chunk_bits, chunk_dst, frame_bytes, frame_off, running,
+                                       done_counter, out_cap, err);
+    return cudaGetLastError();
+}
+
+cudaError_t m1k_launch_stitch(const M1Geom &g, int n_frames, int blocks_x, const uint32_t *staging,
+                              const uint32_t *chunk_bits, const uint32_t *chunk_dst,
+                              const uint32_t *frame_bytes, const unsigned long long *frame_off,
+                              uint8_t *out, unsigned long long out_cap, cudaStream_t st)
+{
+    dim3 grid(blocks_x, n_frames);
+    k_stitch<<<grid, 256, 0, st>>>(g, staging, chunk_bits, chunk_dst, frame_bytes, frame_off, out, out_cap);
+    return cudaGetLastError();
+}
+
+cudaError_t m1k_launch_planes(const uint8_t *rgb, int channels, size_t npix, uint8_t *Y, uint8_t *Cb, uint8_t *Cr,
+                              cudaStream_t st)
+{
+    const int blocks = (int)((npix + 255) / 256 < 148 * 8 ? (npix + 255) / 256 : 148 * 8);
+    k_ycbcr_planes<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(rgb, channels, npix, Y, Cb, Cr);
+    return cudaGetLastError();
+}
+
+cudaError_t m1k_launch_synth(uint32_t seed, long first_frame, int n_frames, int W, int H, int kind,
+                             uint8_t *rgb, cudaStream_t st)
+{
+    k_synth_rgb<<<148 * 8, 256, 0, st>>>(seed, first_frame, n_frames, W, H, kind, rgb);
+    return cudaGetLastError();
+}
+
+void m1k_fill_tables(M1Tables *t)
+{
+    for (int i = 0; i < 112; ++i) t->ac[i] = i < M1_AC_ENTRIES ? kM1AcTable[i] : 0u;
+    for (int i = 0; i < 18; ++i) t->dc[i] = kM1DcSize[i];
+    for (int i = 0; i < 36; ++i) t->first[i] = i < 33 ? kM1AcFirst[i] : 0;
+}

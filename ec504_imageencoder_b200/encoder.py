@@ -1,0 +1,199 @@
+"""Python host layer over the C ABI (include/m1cu.h).
+
+PyTorch is used for plumbing only: device buffers, streams and (in bench.py) torch.distributed.
+Every byte of output is produced by the CUDA kernels in csrc/ through the C ABI; there is no
+CPU fallback and no oracle on this path.
+
+Reference interface mirrored: the per-picture loop body of `mpeg_encode_procedure`
+(reference include/encoder.h:216-445) and its quality argument (include/encoder.h:20,
+default 12 from main.c:16).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _native
+
+MODE_FULL = 0        # raster macroblocks, 4:2:0 chroma (BASELINE configs)
+MODE_REF_COMPAT = 1  # literal traversal of include/encoder.h:238-443 (drop-in byte parity)
+SYNTH_NATURAL, SYNTH_NOISE = 0, 1
+DEFAULT_QUALITY = 12  # reference main.c:16
+
+_ERRORS = {-1: "bad argument", -2: "CUDA failure / no device", -3: "output capacity",
+           -4: "coded AC level outside the reference's encodable range (|L| >= 256)"}
+
+
+class M1Error(RuntimeError):
+    def __init__(self, code: int, detail: str = ""):
+        self.code = code
+        super().__init__(f"m1cu error {code} ({_ERRORS.get(code, '?')}): {detail}")
+
+
+def qmatrix(quality: int) -> np.ndarray:
+    """scale_quantization_matrix (reference source/image_processing.c:314-343), raster order."""
+    out = np.zeros(64, np.int32)
+    _native.m1cu().m1cu_qmatrix(int(quality), out.ctypes.data)
+    return out
+
+
+@dataclass
+class EncodedBatch:
+    """Device-resident result of one encode call."""
+    out: torch.Tensor            # uint8, payloads at 16-byte-aligned offsets
+    frame_bytes: torch.Tensor    # int32 [n] (bit pattern of uint32)
+    frame_offsets: torch.Tensor  # int64 [n+1]
+    levels: torch.Tensor | None  # int16 [n, macroblocks, 6, 64] or None
+
+    def payloads(self) -> list[bytes]:
+        """Copies the payloads to the host (synchronises)."""
+        sizes = self.frame_bytes.cpu().numpy().astype(np.int64)
+        offs = self.frame_offsets.cpu().numpy()
+        end = int(offs[-1])
+        buf = self.out[:end].cpu().numpy()
+        return [buf[int(o):int(o) + int(s)].tobytes() for o, s in zip(offs[:-1], sizes)]
+
+
+class M1Encoder:
+    """One context per GPU.  Geometry and quality are fixed at construction."""
+
+    def __init__(self, width: int, height: int, channels: int = 3, mode: int = MODE_FULL,
+                 quality: int = DEFAULT_QUALITY, max_frames: int = 64, device: int | None = None):
+        self.lib = _native.m1cu()
+        if self.lib.m1cu_device_count() == 0 or not torch.cuda.is_available():
+            raise M1Error(-2, "no CUDA device: the encode path has no CPU fallback")
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.width, self.height, self.channels = int(width), int(height), int(channels)
+        self.mode, self.quality, self.max_frames = int(mode), int(quality), int(max_frames)
+        h = C.c_void_p()
+        rc = self.lib.m1cu_create(C.byref(h), self.device, self.width, self.height, self.channels,
+                                  self.mode, self.quality, self.max_frames)
+        if rc != 0:
+            raise M1Error(rc, (self.lib.m1cu_last_error(None) or b"").decode())
+        self._h = h
+        self.macroblocks = self.lib.m1cu_macroblocks_per_frame(h)
+        self.frame_bytes_in = self.lib.m1cu_frame_bytes_in(h)
+        self.payload_bound = self.lib.m1cu_payload_bound(h)
+        self._stream = None
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.m1cu_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _err(self, rc):
+        raise M1Error(rc, (self.lib.m1cu_last_error(self._h) or b"").decode())
+
+    def _bind_stream(self):
+        # torch's default stream has handle 0 (the legacy default stream); the C ABI reads NULL as
+        # "use your own stream", so name the legacy stream explicitly (cudaStreamLegacy == 0x1).
+        s = torch.cuda.current_stream(self.device).cuda_stream or 1
+        if s != self._stream:
+            rc = self.lib.m1cu_set_stream(self._h, C.c_void_p(s))
+            if rc:
+                self._err(rc)
+            self._stream = s
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.m1cu_launch_count(self._h))
+
+    def typical_out_bytes(self, n_frames: int) -> int:
+        return int(self.lib.m1cu_typical_out_bytes(self._h, int(n_frames)))
+
+    # -- device-resident hot path ------------------------------------------------------------
+    def alloc_outputs(self, n_frames: int, want_levels: bool = False, out_bytes: int | None = None) -> EncodedBatch:
+        dev = torch.device("cuda", self.device)
+        cap = self.typical_out_bytes(n_frames) if out_bytes is None else int(out_bytes)
+        return EncodedBatch(
+            out=torch.empty(cap, dtype=torch.uint8, device=dev),
+            frame_bytes=torch.empty(n_frames, dtype=torch.int32, device=dev),
+            frame_offsets=torch.empty(n_frames + 1, dtype=torch.int64, device=dev),
+            levels=(torch.empty((n_frames, self.macroblocks, 6, 64), dtype=torch.int16, device=dev)
+                    if want_levels else None))
+
+    def encode_device(self, rgb: torch.Tensor, res: EncodedBatch | None = None, want_levels: bool = False,
+                      check: bool = True) -> EncodedBatch:
+        """rgb: uint8 CUDA tensor [n, H, W, C] (contiguous).  Asynchronous unless check=True."""
+        assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
+        n = rgb.shape[0]
+        assert tuple(rgb.shape[1:]) == (self.height, self.width, self.channels), rgb.shape
+        if res is None:
+            res = self.alloc_outputs(n, want_levels)
+        self._bind_stream()
+        rc = self.lib.m1cu_encode_device(self._h, rgb.data_ptr(), n, res.out.data_ptr(), res.out.numel(),
+                                         res.frame_bytes.data_ptr(), res.frame_offsets.data_ptr(),
+                                         res.levels.data_ptr() if res.levels is not None else None)
+        if rc:
+            self._err(rc)
+        if check:
+            self.check()
+        return res
+
+    def check(self):
+        rc = self.lib.m1cu_check(self._h)
+        if rc:
+            self._err(rc)
+
+    # -- host-buffer path (what the C driver uses) ---------------------------------------------
+    def encode_host(self, rgb: np.ndarray | torch.Tensor, want_levels: bool = False, out: np.ndarray | None = None):
+        """rgb: uint8 host array/tensor [n, H, W, C].  Returns (payload list, levels or None)."""
+        if isinstance(rgb, torch.Tensor):
+            assert not rgb.is_cuda
+            src_ptr, n, keep = rgb.data_ptr(), rgb.shape[0], rgb
+            assert rgb.is_contiguous() and rgb.dtype == torch.uint8
+        else:
+            keep = np.ascontiguousarray(rgb, dtype=np.uint8)
+            src_ptr, n = keep.ctypes.data, keep.shape[0]
+        assert tuple(keep.shape[1:]) == (self.height, self.width, self.channels), keep.shape
+        cap = self.typical_out_bytes(n)
+        for _ in range(2):
+            buf = out if out is not None and out.size >= cap else np.empty(cap, np.uint8)
+            sizes = np.zeros(n, np.uint32)
+            lev = np.empty((n, self.macroblocks, 6, 64), np.int16) if want_levels else None
+            total = C.c_size_t(0)
+            self._bind_stream()
+            rc = self.lib.m1cu_encode_host(self._h, src_ptr, n, buf.ctypes.data, buf.size, sizes.ctypes.data,
+                                           lev.ctypes.data if lev is not None else None, C.byref(total))
+            if rc == -3 and cap < self.payload_bound * n:
+                cap = self.payload_bound * n
+                out = None
+                continue
+            if rc:
+                self._err(rc)
+            break
+        offs = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))])
+        payloads = [buf[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(n)]
+        return payloads, lev
+
+    # -- utilities ---------------------------------------------------------------------------------
+    def synth_rgb(self, seed: int, first_frame: int, n_frames: int, kind: int = SYNTH_NATURAL) -> torch.Tensor:
+        dev = torch.device("cuda", self.device)
+        t = torch.empty((n_frames, self.height, self.width, 3), dtype=torch.uint8, device=dev)
+        self._bind_stream()
+        rc = self.lib.m1cu_synth_rgb(self._h, int(seed) & 0xFFFFFFFF, int(first_frame), int(n_frames), int(kind),
+                                     t.data_ptr())
+        if rc:
+            self._err(rc)
+        return t
+
+    def ycbcr_planes(self, rgb: torch.Tensor):
+        """Full-resolution Y, Cb, Cr planes of ONE picture [H, W, C] (the .bit side-file content)."""
+        assert rgb.is_cuda and rgb.dtype == torch.uint8 and rgb.is_contiguous()
+        dev = rgb.device
+        planes = [torch.empty((self.height, self.width), dtype=torch.uint8, device=dev) for _ in range(3)]
+        self._bind_stream()
+        rc = self.lib.m1cu_ycbcr_planes(self._h, rgb.data_ptr(), *[p.data_ptr() for p in planes])
+        if rc:
+            self._err(rc)
+        return planes

@@ -1,0 +1,138 @@
+/*
+ * m1cu.h -- thin C ABI between the host C encoder and the sm_100a CUDA path.
+ *
+ * This is the drop-in boundary for the reference's per-picture loop body,
+ * include/encoder.h:216-445 (convert_rgb_to_ycbcr -> subsampling_420 -> per macroblock
+ * extract_8x8_block / fast_DCT / quantization / zigzag_scanning / run_length_encode /
+ * encode_block_header_i / encode_block_end -> slice padding).  Everything above that loop
+ * (file I/O, JPEG decode, pack/system/packet/sequence/GOP/picture headers, packet-length patch)
+ * stays host C and calls in here through these entry points only.
+ *
+ * Conventions: extern "C", plain pointers and sizes, int return codes (M1CU_OK == 0, negative on
+ * failure, same spirit as the reference's 0 / -1), no exceptions, one context per GPU.  Work is
+ * stream-ordered on the context's stream.  There is NO CPU fallback: without a CUDA device every
+ * entry point that computes fails with M1CU_ERR_CUDA.
+ *
+ * Reference interfaces each entry point replaces (paths relative to the reference checkout):
+ *   m1cu_qmatrix            scale_quantization_matrix   source/image_processing.c:314-343
+ *   m1cu_encode_device/host the loop body               include/encoder.h:216-445, i.e.
+ *                           convert_rgb_to_ycbcr        source/image_processing.c:68-110
+ *                           subsampling_420             source/image_processing.c:114-133
+ *                           extract_8x8_block           source/image_processing.c:138-150
+ *                           fast_DCT                    source/image_processing.c:192-307
+ *                           quantization                source/image_processing.c:349-370
+ *                           zigzag_scanning             source/image_processing.c:373-381
+ *                           run_length_encode           source/image_processing.c:703-751
+ *                           VLC_encode                  source/image_processing.c:400-433
+ *                           mpeg1_slice                 source/mpeg1_blk.c:12-20
+ *                           encode_macroblock_header_i  source/mpeg1_blk.c:38-58
+ *                           encode_block_header_i       source/mpeg1_blk.c:67-113
+ *                           encode_block_end            source/mpeg1_blk.c:115-117
+ *                           encode_blk_coeff            source/vlc.c:315-385
+ *                           encode_coeff_sz_fast        source/vlc.c:146-157
+ *                           bitvector_* (bit order)     source/bit_vector.c:13-121
+ *   m1cu_ycbcr_planes       write_to_bitstream's input  source/image_processing.c:753-787
+ */
+#ifndef M1CU_H
+#define M1CU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define M1CU_ABI_VERSION 1
+
+enum m1cu_mode {
+    M1CU_MODE_FULL       = 0, /* raster macroblocks over the coded frame, 4:2:0 chroma          */
+    M1CU_MODE_REF_COMPAT = 1  /* the literal traversal of include/encoder.h:238-443 (96x144 ROI) */
+};
+
+enum m1cu_status {
+    M1CU_OK            =  0,
+    M1CU_ERR_ARG       = -1, /* bad argument / geometry                                          */
+    M1CU_ERR_CUDA      = -2, /* CUDA runtime failure or no device (see m1cu_last_error)          */
+    M1CU_ERR_CAPACITY  = -3, /* caller's output buffer too small                                 */
+    M1CU_ERR_LEVEL     = -4  /* a coded AC level had |L| >= 256: the reference returns NULL from
+                                encode_blk_coeff (source/vlc.c:383) and crashes; we report it   */
+};
+
+enum m1cu_synth_kind { M1CU_SYNTH_NATURAL = 0, M1CU_SYNTH_NOISE = 1 };
+
+typedef struct m1cu_ctx m1cu_ctx;
+
+/* ---- host-only helpers (no device needed) ------------------------------------------------ */
+int         m1cu_abi_version(void);
+int         m1cu_device_count(void);                       /* 0 when there is no usable GPU     */
+int         m1cu_qmatrix(int quality_factor, int32_t out[64]);
+const char *m1cu_last_error(const m1cu_ctx *ctx);          /* ctx may be NULL: last global error */
+
+/* ---- context ----------------------------------------------------------------------------- */
+/* width/height: picture size in pixels; channels: bytes per pixel of the interleaved input
+ * (>= 3; R,G,B are the first three, as source/image_processing.c:94-97 indexes them).
+ * max_frames: the largest n_frames a single encode call will be given (sizes the staging). */
+int  m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
+                 int mode, int quality_factor, int max_frames);
+int  m1cu_destroy(m1cu_ctx *ctx);
+int  m1cu_set_stream(m1cu_ctx *ctx, void *cuda_stream);    /* cudaStream_t; NULL = own stream   */
+int  m1cu_synchronize(m1cu_ctx *ctx);
+
+/* geometry / sizing */
+int    m1cu_macroblocks_per_frame(const m1cu_ctx *ctx);
+size_t m1cu_frame_bytes_in(const m1cu_ctx *ctx);           /* width*height*channels             */
+size_t m1cu_payload_bound(const m1cu_ctx *ctx);            /* worst-case payload bytes per frame,
+                                                              multiple of 16                    */
+size_t m1cu_typical_out_bytes(const m1cu_ctx *ctx, int n_frames); /* a comfortable out_cap      */
+
+/* ---- the hot path, device-resident ------------------------------------------------------- */
+/* d_rgb:           n_frames pictures, device memory.
+ * d_out/out_cap:   device buffer receiving the payloads; frame f occupies
+ *                  [d_frame_offsets[f], d_frame_offsets[f] + d_frame_bytes[f]); offsets are
+ *                  16-byte aligned and ascending, d_frame_offsets[n_frames] = end of data.
+ * d_frame_bytes:   n_frames uint32, device.   d_frame_offsets: n_frames + 1 uint64, device.
+ * d_levels:        optional (NULL in production): int16 [n_frames][macroblocks][6][64], the
+ *                  zigzag-ordered quantised levels in coding order (the parity metric).
+ * Asynchronous on the context's stream.  Faults detected on the device (capacity, level) are
+ * reported by the next m1cu_check(). */
+int m1cu_encode_device(m1cu_ctx *ctx, const uint8_t *d_rgb, int n_frames,
+                       uint8_t *d_out, size_t out_cap,
+                       uint32_t *d_frame_bytes, uint64_t *d_frame_offsets, int16_t *d_levels);
+
+/* Synchronises the stream and returns the sticky device-side status (then clears it). */
+int m1cu_check(m1cu_ctx *ctx);
+
+/* ---- the hot path, host buffers (what mpeg_encode_procedure calls) ------------------------- */
+/* h_rgb: n_frames pictures in host memory (pinned memory makes the copies asynchronous).
+ * h_out receives the payloads back to back WITHOUT padding: frame f starts at
+ * sum(h_frame_bytes[0..f)).  h_levels optional as above.  Synchronous.  Returns M1CU_OK or an
+ * error; *total_bytes (optional) = sum of the payload sizes. */
+int m1cu_encode_host(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames,
+                     uint8_t *h_out, size_t out_cap, uint32_t *h_frame_bytes,
+                     int16_t *h_levels, size_t *total_bytes);
+
+/* Full-resolution Y, Cb, Cr planes of one picture (the content of the reference's .bit side
+ * files, source/image_processing.c:753-787).  Device pointers, width*height bytes each. */
+int m1cu_ycbcr_planes(m1cu_ctx *ctx, const uint8_t *d_rgb, uint8_t *d_y, uint8_t *d_cb, uint8_t *d_cr);
+
+/* ---- utilities used by tests and bench.py -------------------------------------------------- */
+/* Seeded synthetic RGB written straight into device memory (3 bytes per pixel), frames
+ * first_frame .. first_frame + n_frames - 1.  Same integer formula as oracle/m1_oracle.c. */
+int m1cu_synth_rgb(m1cu_ctx *ctx, uint32_t seed, long first_frame, int n_frames, int kind, uint8_t *d_rgb);
+
+/* counters: kernels launched by this context since creation (for bench.py's gpu_launches) */
+unsigned long long m1cu_launch_count(const m1cu_ctx *ctx);
+
+/* raw device/pinned memory for C callers that have no CUDA headers (the host encoder) */
+void *m1cu_device_alloc(size_t bytes);
+void  m1cu_device_free(void *p);
+void *m1cu_pinned_alloc(size_t bytes);
+void  m1cu_pinned_free(void *p);
+int   m1cu_memcpy_h2d(void *dst, const void *src, size_t bytes);
+int   m1cu_memcpy_d2h(void *dst, const void *src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* M1CU_H */

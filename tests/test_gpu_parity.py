@@ -1,0 +1,140 @@
+"""GPU parity: the CUDA path through the C ABI vs the oracle, bit for bit.
+
+Integer/byte work => the bar is exact equality of (a) the synthetic input bytes, (b) the
+zigzag-ordered quantised levels, (c) every payload byte, (d) the assembled stream.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+import oracle  # noqa: E402
+from oracle import MODE_FULL, MODE_REF_COMPAT, SYNTH_NATURAL, SYNTH_NOISE  # noqa: E402
+
+
+@pytest.fixture(scope="module")
+def m1():
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    import ec504_imageencoder_b200 as m
+    return m
+
+
+def _encode_both(m1, port, W, H, n, q, kind, mode=MODE_FULL, seed=12345, first=0):
+    enc = m1.M1Encoder(W, H, 3, mode, q, max_frames=n)
+    rgb = enc.synth_rgb(seed, first, n, kind)
+    res = enc.encode_device(rgb, want_levels=True)
+    pay = res.payloads()
+    host = rgb.cpu().numpy()
+    lev = res.levels.cpu().numpy()
+    for f in range(n):
+        assert np.array_equal(host[f], port.synth_rgb(seed, first + f, W, H, kind))
+        rp, rl = port.encode_picture(host[f], q, mode, want_levels=True)
+        assert np.array_equal(lev[f], rl), f"levels differ: {W}x{H} q={q} kind={kind} frame={f}"
+        assert pay[f] == rp, f"payload differs: {W}x{H} q={q} kind={kind} frame={f}"
+    enc.close()
+    return pay
+
+
+@pytest.mark.parametrize("kind", [SYNTH_NATURAL, SYNTH_NOISE])
+@pytest.mark.parametrize("q", [5, 12, 50])
+def test_sif_config0(m1, port, q, kind):
+    """BASELINE configs[0] geometry: 352x240, a few frames per quality."""
+    _encode_both(m1, port, 352, 240, 3, q, kind)
+
+
+@pytest.mark.parametrize("W,H", [(16, 16), (17, 16), (16, 17), (33, 47), (100, 70), (640, 480), (641, 479),
+                                 (1, 1), (2050, 18)])
+def test_ragged_sizes(m1, port, W, H):
+    """Edge replication to the coded size, single/multiple chunks per slice."""
+    _encode_both(m1, port, W, H, 2, 12, SYNTH_NOISE)
+    _encode_both(m1, port, W, H, 1, 50, SYNTH_NATURAL)
+
+
+@pytest.mark.parametrize("q", [1, 12, 50, 75, 89])
+def test_ref_compat(m1, port, q):
+    """Literal traversal of include/encoder.h:238-443 on a 400x600 picture (the fixture size)."""
+    _encode_both(m1, port, 400, 600, 2, q, SYNTH_NOISE, MODE_REF_COMPAT)
+    _encode_both(m1, port, 400, 600, 1, q, SYNTH_NATURAL, MODE_REF_COMPAT)
+    _encode_both(m1, port, 96, 144, 1, q, SYNTH_NOISE, MODE_REF_COMPAT)
+
+
+def test_1080p_one_frame(m1, port):
+    pay = _encode_both(m1, port, 1920, 1080, 1, 12, SYNTH_NATURAL)
+    assert 20_000 < len(pay[0]) < 400_000
+
+
+def test_against_reference_functions(m1, ref):
+    """Same comparison against the UNMODIFIED reference functions when oracle/_ref travelled."""
+    W, H, q = 352, 240, 12
+    enc = m1.M1Encoder(W, H, 3, MODE_FULL, q, max_frames=2)
+    rgb = enc.synth_rgb(7, 0, 2, SYNTH_NOISE)
+    res = enc.encode_device(rgb, want_levels=True)
+    pay, lev, host = res.payloads(), res.levels.cpu().numpy(), rgb.cpu().numpy()
+    for f in range(2):
+        rp, rl = ref.encode_picture(host[f], q, MODE_FULL, want_levels=True)
+        assert np.array_equal(lev[f], rl)
+        assert pay[f] == rp
+
+
+def test_host_path_equals_device_path(m1, port):
+    W, H, n = 352, 240, 4
+    enc = m1.M1Encoder(W, H, 3, MODE_FULL, 12, max_frames=n)
+    rgb = enc.synth_rgb(99, 10, n, SYNTH_NATURAL)
+    dev = enc.encode_device(rgb).payloads()
+    hp, lev = enc.encode_host(rgb.cpu().numpy(), want_levels=True)
+    assert hp == dev
+    assert lev.shape == (n, enc.macroblocks, 6, 64)
+    # 4-channel input: the 4th byte is ignored (source/image_processing.c:94-97 indexes i*channels)
+    enc4 = m1.M1Encoder(W, H, 4, MODE_FULL, 12, max_frames=n)
+    rgba = np.concatenate([rgb.cpu().numpy(), np.full((n, H, W, 1), 77, np.uint8)], axis=3)
+    hp4, _ = enc4.encode_host(rgba)
+    assert hp4 == dev
+
+
+def test_color_all_2_24(m1, port):
+    """Every RGB triple through the device colour conversion (the only floating point on the path)."""
+    enc = m1.M1Encoder(4096, 4096, 3, MODE_FULL, 12, max_frames=1)
+    v = torch.arange(256, dtype=torch.uint8, device="cuda")
+    r, g, b = torch.meshgrid(v, v, v, indexing="ij")
+    rgb = torch.stack([r, g, b], dim=-1).reshape(4096, 4096, 3).contiguous()
+    Y, Cb, Cr = enc.ycbcr_planes(rgb)
+    enc.check()
+    oy, ocb, ocr = port.rgb_to_ycbcr(rgb.cpu().numpy().reshape(-1, 3))
+    assert np.array_equal(Y.cpu().numpy().ravel(), oy)
+    assert np.array_equal(Cb.cpu().numpy().ravel(), ocb)
+    assert np.array_equal(Cr.cpu().numpy().ravel(), ocr)
+
+
+def test_unencodable_level_reported(m1, port):
+    """quality 91 + a half-block vertical step gives a coded AC level of 308: the reference
+    returns NULL from encode_blk_coeff and crashes (source/vlc.c:383); the oracle refuses the
+    input and the library reports M1CU_ERR_LEVEL instead."""
+    W = H = 16
+    enc = m1.M1Encoder(W, H, 3, MODE_FULL, 91, max_frames=1)
+    img = np.zeros((1, H, W, 3), np.uint8)
+    img[0, 0:4] = 255
+    img[0, 8:12] = 255
+    with pytest.raises(ValueError):
+        port.encode_picture(img[0], 91, MODE_FULL)
+    with pytest.raises(m1.M1Error) as ei:
+        enc.encode_host(img)
+    assert ei.value.code == -4
+    # one quality step lower the same picture is inside the reference's envelope and must match
+    enc89 = m1.M1Encoder(W, H, 3, MODE_FULL, 89, max_frames=1)
+    hp, _ = enc89.encode_host(img)
+    assert hp[0] == port.encode_picture(img[0], 89, MODE_FULL)
+
+
+def test_capacity_error_and_retry(m1, port):
+    W, H = 64, 64
+    enc = m1.M1Encoder(W, H, 3, MODE_FULL, 50, max_frames=2)
+    rgb = enc.synth_rgb(5, 0, 2, SYNTH_NOISE)
+    tiny = enc.alloc_outputs(2, out_bytes=64)
+    with pytest.raises(m1.M1Error) as ei:
+        enc.encode_device(rgb, res=tiny)
+    assert ei.value.code == -3
+    ok = enc.encode_device(rgb)          # context still usable afterwards
+    host = rgb.cpu().numpy()
+    assert ok.payloads() == [port.encode_picture(host[f], 50, MODE_FULL) for f in range(2)]
