@@ -9,6 +9,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 namespace {
 
@@ -49,6 +50,11 @@ struct m1cu_ctx {
     uint8_t *h_out = nullptr;  size_t h_out_cap = 0;       // pinned bounce buffer
     uint32_t *h_fbytes = nullptr; unsigned long long *h_foff = nullptr; int h_meta_frames = 0;
     unsigned long long launches = 0;
+    // optional per-kernel timing (m1cu_enable_timing)
+    bool timing = false;
+    struct Span { cudaEvent_t a, b; int kind; };
+    std::vector<Span> spans;          // recorded, not yet read
+    std::vector<cudaEvent_t> pool;    // recycled events
     char err[256] = "";
 };
 
@@ -81,16 +87,32 @@ bool make_quant(const int32_t qm[64], M1Quant *q)
         const int S = 19 + fl;
         const long long one = 1ll << S;
         const int K = (int)((one + m - 1) / m);
-        q->mul[k] = K; q->shift[k] = S; q->mask[k] = (int)(one - 1);
+        q->mul[k] = K; q->shift[k] = S; q->ta[k] = m - 1; q->tb[k] = 2 * m - 2;
         for (int c = -2047; c <= 2047; ++c) {
             const long long prod = (long long)c * K + ((c < 0) ? (one - 1) : 0);
             if (prod > 0x7fffffffll || prod < -0x80000000ll) return false;
             const int got = (int)(prod >> S);
             if (got != c / m) return false;
+            if (((unsigned)(c + q->ta[k]) > (unsigned)q->tb[k]) != (c / m != 0)) return false;
         }
     }
     return true;
 }
+
+cudaEvent_t take_event(m1cu_ctx *ctx)
+{
+    cudaEvent_t e = nullptr;
+    if (!ctx->pool.empty()) { e = ctx->pool.back(); ctx->pool.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
+// brackets one launch with events when timing is on
+struct Timed {
+    m1cu_ctx *c; int kind; cudaEvent_t a = nullptr;
+    Timed(m1cu_ctx *ctx, int k) : c(ctx), kind(k) { if (c->timing) { a = take_event(c); cudaEventRecord(a, c->stream); } }
+    ~Timed() { if (a) { cudaEvent_t b = take_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({a, b, kind}); } }
+};
 
 int ensure(m1cu_ctx *ctx, void **p, size_t *cap, size_t need, bool pinned = false)
 {
@@ -165,6 +187,8 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     g.mbs_per_frame = g.mbs_per_slice * g.slices;
     g.chunk_stride = (unsigned)align_up(((size_t)M1_SLICE_HDR_BITS + (size_t)g.chunk_mbs * M1_MB_MAX_BITS + 7) / 8 + 8, 16);
     g.frame_stride = (unsigned long long)width * height * channels;
+    // 128-bit tile loads need 16-pixel tiles to start on 16-byte boundaries in every row and picture
+    g.fast_load = (mode == M1CU_MODE_FULL && (channels == 3 || channels == 4) && width % 16 == 0) ? channels : 0;
 
     m1cu_qmatrix(quality, ctx->qm);
     if (!make_quant(ctx->qm, &ctx->q)) { delete ctx; return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: quantiser constants failed self-check"); }
@@ -190,7 +214,7 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     CUC(cudaMemset(ctx->d_done, 0, sizeof(unsigned int)));
     CUC(cudaMemset(ctx->d_running, 0, sizeof(unsigned long long)));
     M1Tables ht;
-    m1k_fill_tables(&ht);
+    m1k_fill_tables(&ht, ctx->q);
     CUC(cudaMemcpy(ctx->d_tables, &ht, sizeof ht, cudaMemcpyHostToDevice));
     CUC(m1k_prepare(g));
 #undef CUC
@@ -210,6 +234,8 @@ int m1cu_destroy(m1cu_ctx *ctx)
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_fbytes) cudaFreeHost(ctx->h_fbytes);
     if (ctx->h_foff) cudaFreeHost(ctx->h_foff);
+    for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+    for (auto e : ctx->pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
     return M1CU_OK;
@@ -262,7 +288,8 @@ int m1cu_encode_device(m1cu_ctx *ctx, const uint8_t *d_rgb, int n_frames, uint8_
         return fail(ctx, M1CU_ERR_ARG, "m1cu_encode_device: bad argument");
     if (n_frames > ctx->max_frames) return fail(ctx, M1CU_ERR_ARG, "m1cu_encode_device: n_frames > max_frames");
     if (((uintptr_t)d_out & 15) != 0) return fail(ctx, M1CU_ERR_ARG, "m1cu_encode_device: d_out must be 16-byte aligned");
-    const M1Geom &g = ctx->g;
+    M1Geom g = ctx->g;
+    if (((uintptr_t)d_rgb & 15) != 0) g.fast_load = 0;          // unaligned input: generic loads
     cudaStream_t st = ctx->stream;
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemsetAsync(ctx->d_running, 0, sizeof(unsigned long long), st));
@@ -271,14 +298,23 @@ int m1cu_encode_device(m1cu_ctx *ctx, const uint8_t *d_rgb, int n_frames, uint8_
     if (bx > 128) bx = 128;
     for (int f0 = 0; f0 < n_frames; f0 += ctx->batch_frames) {
         const int nb = n_frames - f0 < ctx->batch_frames ? n_frames - f0 : ctx->batch_frames;
-        CU(m1k_launch_encode(g, ctx->q, d_rgb + (size_t)f0 * g.frame_stride, nb, ctx->d_tables, ctx->d_staging,
-                             ctx->d_chunk_bits, d_levels ? d_levels + (size_t)f0 * g.mbs_per_frame * 384 : nullptr,
-                             ctx->d_err, st));
-        CU(m1k_launch_layout(g, nb, ctx->d_chunk_bits, ctx->d_chunk_dst, d_frame_bytes + f0,
-                             (unsigned long long *)d_frame_offsets + f0, ctx->d_running, ctx->d_done,
-                             (unsigned long long)out_cap, ctx->d_err, st));
-        CU(m1k_launch_stitch(g, nb, bx, ctx->d_staging, ctx->d_chunk_bits, ctx->d_chunk_dst, d_frame_bytes + f0,
-                             (const unsigned long long *)d_frame_offsets + f0, d_out, (unsigned long long)out_cap, st));
+        {
+            Timed t(ctx, 0);
+            CU(m1k_launch_encode(g, ctx->q, d_rgb + (size_t)f0 * g.frame_stride, nb, ctx->d_tables, ctx->d_staging,
+                                 ctx->d_chunk_bits, d_levels ? d_levels + (size_t)f0 * g.mbs_per_frame * 384 : nullptr,
+                                 ctx->d_err, st));
+        }
+        {
+            Timed t(ctx, 1);
+            CU(m1k_launch_layout(g, nb, ctx->d_chunk_bits, ctx->d_chunk_dst, d_frame_bytes + f0,
+                                 (unsigned long long *)d_frame_offsets + f0, ctx->d_running, ctx->d_done,
+                                 (unsigned long long)out_cap, ctx->d_err, st));
+        }
+        {
+            Timed t(ctx, 2);
+            CU(m1k_launch_stitch(g, nb, bx, ctx->d_staging, ctx->d_chunk_bits, ctx->d_chunk_dst, d_frame_bytes + f0,
+                                 (const unsigned long long *)d_frame_offsets + f0, d_out, (unsigned long long)out_cap, st));
+        }
         ctx->launches += 3;
     }
     return M1CU_OK;
@@ -377,6 +413,27 @@ int m1cu_synth_rgb(m1cu_ctx *ctx, uint32_t seed, long first_frame, int n_frames,
 }
 
 unsigned long long m1cu_launch_count(const m1cu_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+int m1cu_enable_timing(m1cu_ctx *ctx, int on)
+{
+    if (!ctx) return M1CU_ERR_ARG;
+    ctx->timing = on != 0;
+    return M1CU_OK;
+}
+
+int m1cu_kernel_times(m1cu_ctx *ctx, double ms[3], unsigned long long n[3])
+{
+    if (!ctx || !ms || !n) return M1CU_ERR_ARG;
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 3; ++k) { ms[k] = 0.0; n[k] = 0; }
+    for (auto &s : ctx->spans) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) { ms[s.kind] += t; n[s.kind] += 1; }
+        ctx->pool.push_back(s.a); ctx->pool.push_back(s.b);
+    }
+    ctx->spans.clear();
+    return M1CU_OK;
+}
 
 void *m1cu_device_alloc(size_t bytes) { void *p = nullptr; if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 void  m1cu_device_free(void *p) { if (p) cudaFree(p); }

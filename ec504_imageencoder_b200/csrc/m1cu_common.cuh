@@ -24,6 +24,7 @@ enum { M1_ERRBIT_CAPACITY = 1, M1_ERRBIT_LEVEL = 2 };
 struct M1Geom {
     int W, H, channels;
     int mode;                  // M1CU_MODE_*
+    int fast_load;             // 3 / 4: channels with 16-byte-aligned 16-pixel tiles, 0: generic loads only
     int slices;                // per picture
     int mbs_per_slice;
     int chunk_mbs;             // macroblocks per chunk (last chunk of a slice may hold fewer)
@@ -34,17 +35,20 @@ struct M1Geom {
     unsigned long long frame_stride;   // input bytes per picture
 };
 
-// Quantiser constants for raster position k: level = (c * mul + ((c >> 31) & mask)) >> shift
+// Quantiser constants for raster position k: level = (c * mul + ((c >> 31) & ((1 << shift) - 1))) >> shift
 // == C truncating division c / m (source/image_processing.c:367) for |c| <= 2047; checked
 // exhaustively on the host when the context is created.
 struct M1Quant {
     int mul[64];
-    int mask[64];
     int shift[64];
+    int ta[64];                // m - 1
+    int tb[64];                // 2m - 2 : level != 0  <=>  (unsigned)(c + ta) > tb
 };
 
 struct M1Tables {
     uint32_t ac[112];
     uint32_t dc[18];
     uint8_t  first[36];
+    int      qmul[64];         // quantiser constants in ZIGZAG order (for the coder's dynamic index)
+    int      qshift[64];
 };

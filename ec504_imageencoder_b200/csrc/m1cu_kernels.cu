@@ -13,20 +13,32 @@
 // truncates.  __dmul_rn/__dadd_rn/__dsub_rn are never contracted into FMAs, so this is the same
 // arithmetic bit for bit.
 // -------------------------------------------------------------------------------------------
+// int -> double and double -> int go through the 2^52 mantissa trick instead of I2F/F2I (those run
+// on the 16-lane/SM XU pipe): 2^52 + v holds v in its low word, and adding 2^52 with round-toward-
+// zero leaves trunc(x) there (x >= 0 always holds here: Y >= 0, Cb, Cr >= 0.5).  0.5*x is exact, so
+// fma(0.5, x, acc) rounds once exactly like the reference's separate multiply and add.
+__device__ __forceinline__ double u8_to_double(int v)
+{
+    return __dsub_rn(__hiloint2double(0x43300000, v), 4503599627370496.0);
+}
+__device__ __forceinline__ int trunc_nonneg(double x)
+{
+    return __double2loint(__dadd_rz(x, 4503599627370496.0));
+}
 __device__ __forceinline__ void ycbcr_exact(int r, int g, int b, int &y, int &cb, int &cr)
 {
-    const double rd = __int2double_rn(r), gd = __int2double_rn(g), bd = __int2double_rn(b);
+    const double rd = u8_to_double(r), gd = u8_to_double(g), bd = u8_to_double(b);
     double t = __dadd_rn(__dmul_rn(0.299, rd), __dmul_rn(0.587, gd));
     t = __dadd_rn(t, __dmul_rn(0.114, bd));
-    y = __double2int_rz(t);
+    y = trunc_nonneg(t);
     double u = __dsub_rn(128.0, __dmul_rn(0.168736, rd));
     u = __dsub_rn(u, __dmul_rn(0.331264, gd));
-    u = __dadd_rn(u, __dmul_rn(0.5, bd));
-    cb = __double2int_rz(u);
-    double v = __dadd_rn(128.0, __dmul_rn(0.5, rd));
+    u = __fma_rn(0.5, bd, u);
+    cb = trunc_nonneg(u);
+    double v = __fma_rn(0.5, rd, 128.0);
     v = __dsub_rn(v, __dmul_rn(0.418688, gd));
     v = __dsub_rn(v, __dmul_rn(0.081312, bd));
-    cr = __double2int_rz(v);
+    cr = trunc_nonneg(v);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -113,14 +125,52 @@ __host__ __device__ constexpr int zz_raster(int z)
 }
 
 // -------------------------------------------------------------------------------------------
+// Shared-memory plane layout.  Samples are int32, block-major: block `blk` owns 64 words; its
+// sixteen 16-byte chunks (chunk i = row*2 + (col>>2)) are XOR-swizzled with a per-block key so
+// that both the producers (16x2-pixel colour tiles, 128-bit stores) and the consumers (one thread
+// per block, 128-bit loads) are bank-conflict free.
+//   luma blocks:   blk = by * 2C + bc      (by = block row 0/1 of the macroblock row, bc = 8-pixel column)
+//   chroma blocks: blk = 4C + mb (Cb), 5C + mb (Cr)                       C = chunk_mbs
+// Consumer thread t handles block t.  After a thread has pulled its block into registers it
+// reuses the first 128 bytes of the same 256 bytes for its DCT-coefficient record (int16, zigzag).
+// -------------------------------------------------------------------------------------------
+__device__ __forceinline__ int blk_key(int blk) { return (blk ^ (blk >> 3)) & 7; }
+__device__ __forceinline__ int chunk_word(int blk, int i)      // first word of chunk i of block blk
+{
+    return blk * 64 + (((i & 8) | ((i & 7) ^ blk_key(blk))) << 2);
+}
+__device__ __forceinline__ int plane_word(int blk, int r, int c)
+{
+    return chunk_word(blk, r * 2 + (c >> 2)) + (c & 3);
+}
+// coefficient record of thread t: 64 shorts at byte offset t*256, 16-byte groups swizzled by t
+__device__ __forceinline__ int rec_index(int t, int z)
+{
+    return t * 128 + ((((z >> 3) ^ t) & 7) << 3) + (z & 7);
+}
+
+// -------------------------------------------------------------------------------------------
 // Bit sinks for the block coder.
 // -------------------------------------------------------------------------------------------
-struct BitCounter {
+// First 64 bits of a block in registers (typical blocks are 5..40 bits); n keeps counting past 64
+// so the length is always exact, the bits are only valid while n <= 64.
+struct BitAcc {
+    uint32_t hi, lo;
     int n;
-    __device__ __forceinline__ void put(uint32_t, int len) { n += len; }
+    __device__ __forceinline__ void put(uint32_t code, int len)
+    {
+        const int end = n + len;
+        if (end <= 32) {
+            hi |= code << (32 - end);
+        } else if (end <= 64) {
+            if (n < 32) hi |= code >> (end - 32);
+            lo |= code << (64 - end);
+        }
+        n = end;
+    }
 };
 
-// Writes MSB-first into a shared-memory window of logical 32-bit words covering stream bits
+// Streams MSB-first into a shared-memory window of logical 32-bit words covering chunk bits
 // [w0, w0 + 32*M1_WIN_WORDS); bits outside the window are dropped (another pass takes them).
 struct WindowWriter {
     uint32_t *win;
@@ -139,25 +189,27 @@ struct WindowWriter {
     }
 };
 
-// 16-byte-chunk XOR swizzle of a thread's 128-byte level record (conflict-free 128-bit stores)
-__device__ __forceinline__ int lvl_index(int tid, int z)
+// quantised level of zigzag position z from the DCT coefficient c: C truncating division by the
+// scaled matrix entry (source/image_processing.c:367), as multiply-shift (see M1Tables).
+__device__ __forceinline__ int quant_level(int c, int z, const M1Tables *tb)
 {
-    return tid * 64 + ((((z >> 3) ^ tid) & 7) << 3) + (z & 7);
+    const int sh = tb->qshift[z];
+    return (c * tb->qmul[z] + ((c >> 31) & ((1 << sh) - 1))) >> sh;
 }
 
 // One block's bits: DC (source/mpeg1_blk.c:67-113), AC walk (source/image_processing.c:400-433,
-// source/vlc.c:315-385), end of block (source/mpeg1_blk.c:115-117).  lv: this thread's zigzag
-// levels in shared memory; nz: bit z set <=> level z non-zero.  Returns non-zero when a coded AC
+// source/vlc.c:315-385), end of block (source/mpeg1_blk.c:115-117).  rec: the shared coefficient
+// records; nz: bit z set <=> quantised level z is non-zero.  Returns non-zero when a coded AC
 // level is outside the reference's encodable range.
 template <class Sink>
-__device__ __forceinline__ int code_block(Sink &s, const short *lv_base, int tid, unsigned long long nz,
+__device__ __forceinline__ int code_block(Sink &s, const short *rec, int tid, unsigned long long nz,
                                           bool is_luma, const M1Tables *tb)
 {
     int bad = 0;
     int prev = -1;
     unsigned long long m = nz;
     if (nz & 1ull) {
-        const int v = lv_base[lvl_index(tid, 0)];
+        const int v = quant_level(rec[rec_index(tid, 0)], 0, tb);
         int c = v < 0 ? -v : v;
         const int low = c & 0xff;
         const int sz = low ? 32 - __clz(low) : 1;            // highest set bit of bits 0..7, default 1
@@ -176,7 +228,7 @@ __device__ __forceinline__ int code_block(Sink &s, const short *lv_base, int tid
     while (m) {
         const int k = __ffsll((long long)m) - 1;
         m &= m - 1ull;
-        const int L = lv_base[lvl_index(tid, k)];
+        const int L = quant_level(rec[rec_index(tid, k)], k, tb);
         const int r = k - prev - 2;                          // run - 1 of source/vlc.c:326
         const int mag = L < 0 ? -L : L;
         const int a = mag - 1;
@@ -200,7 +252,7 @@ __device__ __forceinline__ int code_block(Sink &s, const short *lv_base, int tid
 }
 
 // -------------------------------------------------------------------------------------------
-// k_encode_chunks: one CTA per (chunk, slice, picture).
+// Colour tiles.
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ const uint8_t *px_ptr(const uint8_t *frame, const M1Geom &g, int x, int y)
 {
@@ -209,8 +261,90 @@ __device__ __forceinline__ const uint8_t *px_ptr(const uint8_t *frame, const M1G
     return frame + ((size_t)y * g.W + x) * g.channels;
 }
 
+// byte j (0..16*CH-1) of a 16-pixel row held in w[]
+#define M1_ROW_BYTE(w, j) (((w)[(j) >> 2] >> (8 * ((j) & 3))) & 0xffu)
+
+// Fast tile: 16 pixels x 2 rows of macroblock `k` of the chunk, rows 2*qy, 2*qy+1 of the
+// macroblock row; everything in range and 16-byte aligned.  128-bit loads, conversion-free FP64,
+// 128-bit swizzled stores of int32 samples; the 2x2 chroma mean (source/image_processing.c:126-130)
+// stays inside the thread.
+template <int CH>
+__device__ __forceinline__ void color_tile_fast(const uint8_t *__restrict__ row0, size_t pitch, int k, int qy,
+                                                int C, int *__restrict__ planes)
+{
+    uint32_t w0[4 * CH], w1[4 * CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const uint4 a = __ldg((const uint4 *)row0 + i);
+        w0[4 * i] = a.x; w0[4 * i + 1] = a.y; w0[4 * i + 2] = a.z; w0[4 * i + 3] = a.w;
+    }
+#pragma unroll
+    for (int i = 0; i < CH; ++i) {
+        const uint4 a = __ldg((const uint4 *)(row0 + pitch) + i);
+        w1[4 * i] = a.x; w1[4 * i + 1] = a.y; w1[4 * i + 2] = a.z; w1[4 * i + 3] = a.w;
+    }
+    int sb[8], sr[8];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int rr = 2 * qy + dy, by = rr >> 3, r = rr & 7;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                 // the two 8x8 luma blocks the tile touches
+            const int blk = by * 2 * C + 2 * k + h;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {             // 4-pixel groups = 16-byte chunks
+                int yv[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int i = 8 * h + 4 * j + e;  // pixel 0..15 of the tile row
+                    const uint32_t R = dy ? M1_ROW_BYTE(w1, CH * i) : M1_ROW_BYTE(w0, CH * i);
+                    const uint32_t G = dy ? M1_ROW_BYTE(w1, CH * i + 1) : M1_ROW_BYTE(w0, CH * i + 1);
+                    const uint32_t B = dy ? M1_ROW_BYTE(w1, CH * i + 2) : M1_ROW_BYTE(w0, CH * i + 2);
+                    int cb, cr;
+                    ycbcr_exact((int)R, (int)G, (int)B, yv[e], cb, cr);
+                    if (dy == 0 && (e & 1) == 0) { sb[i >> 1] = cb; sr[i >> 1] = cr; }
+                    else                         { sb[i >> 1] += cb; sr[i >> 1] += cr; }
+                }
+                *(int4 *)(planes + chunk_word(blk, r * 2 + j)) = make_int4(yv[0], yv[1], yv[2], yv[3]);
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        *(int4 *)(planes + chunk_word(4 * C + k, qy * 2 + j)) =
+            make_int4(sb[4 * j] >> 2, sb[4 * j + 1] >> 2, sb[4 * j + 2] >> 2, sb[4 * j + 3] >> 2);
+        *(int4 *)(planes + chunk_word(5 * C + k, qy * 2 + j)) =
+            make_int4(sr[4 * j] >> 2, sr[4 * j + 1] >> 2, sr[4 * j + 2] >> 2, sr[4 * j + 3] >> 2);
+    }
+}
+
+// Generic tile: any alignment / channel count, coordinates clamped to the picture (= edge
+// replication up to the coded size).
+__device__ __noinline__ void color_tile_generic(const uint8_t *__restrict__ fr, const M1Geom &g, int x0, int y0,
+                                                int k, int qy, int C, int *__restrict__ planes)
+{
+    for (int qx = 0; qx < 8; ++qx) {
+        int sb = 0, sr = 0;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 2; ++dx) {
+                const uint8_t *p = px_ptr(fr, g, x0 + 2 * qx + dx, y0 + dy);
+                int yy, cb, cr;
+                ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
+                const int rr = 2 * qy + dy, cc = 2 * qx + dx;
+                planes[plane_word((rr >> 3) * 2 * C + 2 * k + (cc >> 3), rr & 7, cc & 7)] = yy;
+                sb += cb; sr += cr;
+            }
+        planes[plane_word(4 * C + k, qy, qx)] = sb >> 2;
+        planes[plane_word(5 * C + k, qy, qx)] = sr >> 2;
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// k_encode_chunks: one CTA per (chunk, slice, picture).
+// -------------------------------------------------------------------------------------------
 template <bool kLevels>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quant q,
                 const uint8_t *__restrict__ rgb, const M1Tables *__restrict__ gtab,
                 uint32_t *__restrict__ staging, uint32_t *__restrict__ chunk_bits,
@@ -219,18 +353,17 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int chunk = blockIdx.x, slice = blockIdx.y, frame = blockIdx.z;
-    const int mb0 = chunk * g.chunk_mbs;
-    const int nmb = min(g.chunk_mbs, g.mbs_per_slice - mb0);
-    const int ypitch = 16 * g.chunk_mbs, cpitch = 8 * g.chunk_mbs;
+    const int C = g.chunk_mbs;
+    const int mb0 = chunk * C;
+    const int nmb = min(C, g.mbs_per_slice - mb0);
 
     // shared memory carve-up
-    uint8_t *Ys  = smem;                                   // [16][ypitch]
-    uint8_t *Cbs = Ys + 16 * ypitch;                       // [8][cpitch]
-    uint8_t *Crs = Cbs + 8 * cpitch;                       // [8][cpitch]
-    short   *lvl = (short *)(Crs + 8 * cpitch);            // [nthr][64] swizzled
-    uint32_t *win = (uint32_t *)(lvl + (size_t)nthr * 64); // [M1_WIN_WORDS]
-    M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS);
-    int *scan = (int *)(tb + 1);                           // [32] warp totals + [1] chunk total
+    int *planes = (int *)smem;                                   // [6C blocks][64] int32, swizzled
+    short *rec = (short *)smem;                                  // aliases planes (see layout note)
+    uint32_t *win = (uint32_t *)(planes + 6 * C * 64);           // [M1_WIN_WORDS + 2]
+    M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS + 2);
+    int *lens = (int *)(tb + 1);                                 // [256] bits per coding position
+    int *scan = lens + 256;                                      // [32] warp totals, [32] chunk total
 
     for (int i = tid; i < (int)(sizeof(M1Tables) / 4); i += nthr) ((uint32_t *)tb)[i] = ((const uint32_t *)gtab)[i];
 
@@ -238,26 +371,15 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
 
     // ---- phase 1: colour conversion into the chunk's planes --------------------------------
     if (g.mode == 0) {
-        // FULL: slice = macroblock row; chunk covers columns [16*mb0, 16*(mb0+nmb)); chroma is the
-        // truncating mean of each 2x2 (source/image_processing.c:126-130); coordinates are
-        // clamped = edge replication up to the coded size.
-        const int qw = 8 * nmb;
-        for (int qi = tid; qi < 8 * qw; qi += nthr) {
-            const int qy = qi / qw, qx = qi - qy * qw;
-            const int x = 16 * mb0 + 2 * qx, y = 16 * slice + 2 * qy;
-            int sb = 0, sr = 0;
-#pragma unroll
-            for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-                for (int dx = 0; dx < 2; ++dx) {
-                    const uint8_t *p = px_ptr(fr, g, x + dx, y + dy);
-                    int yy, cb, cr;
-                    ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
-                    Ys[(2 * qy + dy) * ypitch + 2 * qx + dx] = (uint8_t)yy;
-                    sb += cb; sr += cr;
-                }
-            Cbs[qy * cpitch + qx] = (uint8_t)(sb >> 2);
-            Crs[qy * cpitch + qx] = (uint8_t)(sr >> 2);
+        // FULL: slice = macroblock row; tile = macroblock k of the chunk, row pair qy.
+        const size_t pitch = (size_t)g.W * g.channels;
+        for (int tile = tid; tile < 8 * nmb; tile += nthr) {
+            const int qy = tile / nmb, k = tile - qy * nmb;
+            const int x0 = 16 * (mb0 + k), y0 = 16 * slice + 2 * qy;
+            const bool inside = (x0 + 16 <= g.W) && (y0 + 2 <= g.H);
+            if (inside && g.fast_load == 3)      color_tile_fast<3>(fr + (size_t)y0 * pitch + (size_t)x0 * 3, pitch, k, qy, C, planes);
+            else if (inside && g.fast_load == 4) color_tile_fast<4>(fr + (size_t)y0 * pitch + (size_t)x0 * 4, pitch, k, qy, C, planes);
+            else                                 color_tile_generic(fr, g, x0, y0, k, qy, C, planes);
         }
     } else {
         // REF_COMPAT (include/encoder.h:238-348): "slice" s is the 16-pixel column x = 16*s, the
@@ -269,7 +391,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
             const uint8_t *p = fr + ((size_t)(16 * (mb0 + mb) + r) * g.W + x0 + c) * g.channels;
             int yy, cb, cr;
             ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
-            Ys[r * ypitch + 16 * mb + c] = (uint8_t)yy;
+            planes[plane_word((r >> 3) * 2 * C + 2 * mb + (c >> 3), r & 7, c & 7)] = yy;
         }
         const int half = g.W / 2;
         for (int i = tid; i < 64 * nmb; i += nthr) {
@@ -278,78 +400,79 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
             const uint8_t *p = fr + off * g.channels;      // pixel `off` of the row-major picture
             int yy, cb, cr;
             ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
-            Cbs[r * cpitch + 8 * mb + c] = (uint8_t)cb;
-            Crs[r * cpitch + 8 * mb + c] = (uint8_t)cr;
+            planes[plane_word(4 * C + mb, r, c)] = cb;
+            planes[plane_word(5 * C + mb, r, c)] = cr;
         }
     }
     __syncthreads();
 
-    // ---- phase 2: one thread per 8x8 block: DCT, quantise, zigzag ---------------------------
-    const int mb = tid / 6, blk = tid - mb * 6;
-    const bool active = mb < nmb;
+    // ---- phase 2: one thread per 8x8 block (thread t = plane block t): DCT, non-zero mask ---------
+    int mb, blk;                                            // macroblock in chunk, block 0..5 in coding order
+    if (tid < 4 * C) { const int by = tid >= 2 * C, bc = tid - by * 2 * C; mb = bc >> 1; blk = by * 2 + (bc & 1); }
+    else             { const int cr = tid >= 5 * C; mb = tid - (4 + cr) * C; blk = 4 + cr; }
+    const bool active = tid < 6 * C && mb < nmb;
     const bool is_luma = blk < 4;
+    const int pos = mb * 6 + blk;                           // coding position within the chunk
     unsigned long long nz = 0;
     if (active) {
         int v[64];
-        const uint8_t *src; int pitch;
-        if (is_luma) { src = Ys + ((blk >> 1) * 8) * ypitch + 16 * mb + (blk & 1) * 8; pitch = ypitch; }
-        else         { src = (blk == 4 ? Cbs : Crs) + 8 * mb; pitch = cpitch; }
+        {
+            const int key4 = blk_key(tid) << 2;
+            const int *src = planes + tid * 64;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const uint2 w = *(const uint2 *)(src + i * pitch);
-            v[i * 8 + 0] = w.x & 0xff; v[i * 8 + 1] = (w.x >> 8) & 0xff;
-            v[i * 8 + 2] = (w.x >> 16) & 0xff; v[i * 8 + 3] = w.x >> 24;
-            v[i * 8 + 4] = w.y & 0xff; v[i * 8 + 5] = (w.y >> 8) & 0xff;
-            v[i * 8 + 6] = (w.y >> 16) & 0xff; v[i * 8 + 7] = w.y >> 24;
+            for (int i = 0; i < 8; ++i) {
+                const int o = ((i << 2) ^ key4);
+                const int4 a = *(const int4 *)(src + o);
+                const int4 b = *(const int4 *)(src + o + 32);
+                v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+                v[32 + 4 * i] = b.x; v[32 + 4 * i + 1] = b.y; v[32 + 4 * i + 2] = b.z; v[32 + 4 * i + 3] = b.w;
+            }
         }
         fdct8x8(v);
-        // quantise: truncating division by the scaled matrix (source/image_processing.c:367)
-#pragma unroll
-        for (int k = 0; k < 64; ++k) {
-            const int c = v[k];
-            v[k] = (c * q.mul[k] + ((c >> 31) & q.mask[k])) >> q.shift[k];
-        }
-        // zigzag (source/image_processing.c:373-381) + pack to int16 + non-zero mask
+        // level != 0  <=>  |c| >= m  <=>  (unsigned)(c + m - 1) > 2m - 2   (m = scaled matrix entry)
         uint32_t lo = 0, hi = 0;
 #pragma unroll
-        for (int z = 0; z < 32; ++z) if (v[zz_raster(z)] != 0) lo |= 1u << z;
+        for (int z = 0; z < 32; ++z) { const int k = zz_raster(z); if ((unsigned)(v[k] + q.ta[k]) > (unsigned)q.tb[k]) lo |= 1u << z; }
 #pragma unroll
-        for (int z = 32; z < 64; ++z) if (v[zz_raster(z)] != 0) hi |= 1u << (z - 32);
+        for (int z = 32; z < 64; ++z) { const int k = zz_raster(z); if ((unsigned)(v[k] + q.ta[k]) > (unsigned)q.tb[k]) hi |= 1u << (z - 32); }
         nz = ((unsigned long long)hi << 32) | lo;
+        // coefficient record: zigzag order (source/image_processing.c:373-381), int16 (|c| <= 2042)
 #pragma unroll
         for (int cidx = 0; cidx < 8; ++cidx) {
             uint4 w;
-            w.x = (uint32_t)(v[zz_raster(cidx * 8 + 0)] & 0xffff) | ((uint32_t)v[zz_raster(cidx * 8 + 1)] << 16);
-            w.y = (uint32_t)(v[zz_raster(cidx * 8 + 2)] & 0xffff) | ((uint32_t)v[zz_raster(cidx * 8 + 3)] << 16);
-            w.z = (uint32_t)(v[zz_raster(cidx * 8 + 4)] & 0xffff) | ((uint32_t)v[zz_raster(cidx * 8 + 5)] << 16);
-            w.w = (uint32_t)(v[zz_raster(cidx * 8 + 6)] & 0xffff) | ((uint32_t)v[zz_raster(cidx * 8 + 7)] << 16);
-            *(uint4 *)(lvl + tid * 64 + (((cidx ^ tid) & 7) << 3)) = w;
+            w.x = __byte_perm(v[zz_raster(cidx * 8 + 0)], v[zz_raster(cidx * 8 + 1)], 0x5410);
+            w.y = __byte_perm(v[zz_raster(cidx * 8 + 2)], v[zz_raster(cidx * 8 + 3)], 0x5410);
+            w.z = __byte_perm(v[zz_raster(cidx * 8 + 4)], v[zz_raster(cidx * 8 + 5)], 0x5410);
+            w.w = __byte_perm(v[zz_raster(cidx * 8 + 6)], v[zz_raster(cidx * 8 + 7)], 0x5410);
+            *(uint4 *)(rec + tid * 128 + (((cidx ^ tid) & 7) << 3)) = w;
         }
     }
+
+    // ---- phase 3: code every block into registers, scan the lengths in coding order ----------
+    BitAcc acc{0u, 0u, 0};
+    int bad = 0;
+    if (active) {
+        if (blk == 0) acc.put(3u, 2);                       // address increment '1' + macroblock_type '1'
+        bad = code_block(acc, rec, tid, nz, is_luma, tb);
+        lens[pos] = acc.n;
+    }
+    if (bad) atomicOr(err, M1_ERRBIT_LEVEL);
     __syncthreads();
 
     if (kLevels) {
-        // debug output: zigzag levels in coding order, [picture][macroblock][6][64]
+        // debug output: quantised zigzag levels in coding order, [picture][macroblock][6][64]
         short *dst = levels + ((size_t)frame * g.mbs_per_frame + (size_t)slice * g.mbs_per_slice + mb0) * 384;
         for (int i = tid; i < nmb * 384; i += nthr) {
-            const int t = i >> 6, z = i & 63;
-            dst[i] = lvl[lvl_index(t, z)];
+            const int p = i >> 6, z = i & 63, m = p / 6, b = p - m * 6;
+            const int t = b < 4 ? (b >> 1) * 2 * C + 2 * m + (b & 1) : (b == 4 ? 4 * C + m : 5 * C + m);
+            dst[i] = (short)quant_level(rec[rec_index(t, z)], z, tb);
         }
     }
 
-    // ---- phase 3: bit lengths, offsets, packing ----------------------------------------------
-    const bool slice_head = active && tid == 0 && chunk == 0;
-    int my_bits = 0, bad = 0;
-    if (active) {
-        BitCounter bc{0};
-        bad = code_block(bc, lvl, tid, nz, is_luma, tb);
-        my_bits = bc.n + (blk == 0 ? 2 : 0) + (slice_head ? M1_SLICE_HDR_BITS : 0);
-    }
-    if (bad) atomicOr(err, M1_ERRBIT_LEVEL);
-
-    // block-wide exclusive scan of my_bits
     const int lane = tid & 31, warp = tid >> 5;
-    int incl = my_bits;
+    const int npos = 6 * nmb;
+    const int mine = tid < npos ? lens[tid] : 0;            // thread i scans coding position i
+    int incl = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, d);
@@ -359,7 +482,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
     __syncthreads();
     if (warp == 0) {
         const int nw = (nthr + 31) >> 5;
-        int w = lane < nw ? scan[lane] : 0;
+        const int w = lane < nw ? scan[lane] : 0;
         int wi = w;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
@@ -370,23 +493,38 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
         if (lane == 31) scan[32] = wi;
     }
     __syncthreads();
-    const int my_off = scan[warp] + incl - my_bits;
-    const int total_bits = scan[32];
+    const int hdr_bits = chunk == 0 ? M1_SLICE_HDR_BITS : 0;
+    if (tid < npos) lens[tid] = hdr_bits + scan[warp] + incl - mine;   // exclusive offset of position tid
+    const int total_bits = hdr_bits + scan[32];
+    __syncthreads();
+    const int my_off = active ? lens[pos] : 0;
+    const int my_bits = acc.n;
 
     uint32_t *out = staging + ((size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk)
                                   * (g.chunk_stride / 4);
     for (int w0 = 0; w0 < total_bits; w0 += 32 * M1_WIN_WORDS) {
-        for (int i = tid; i < M1_WIN_WORDS; i += nthr) win[i] = 0;
+        for (int i = tid; i < M1_WIN_WORDS + 2; i += nthr) win[i] = 0;
         __syncthreads();
+        if (tid == 0 && hdr_bits && w0 == 0) {
+            // source/mpeg1_blk.c:12-20: 000001 | (vertical_pos+1)&0xff | quant_scale(5)=1 | 0
+            WindowWriter ww{win, 0, 0};
+            ww.put(1u, 24);
+            ww.put(((((uint32_t)(slice & 0xff) + 1u) & 0xffu) << 6) | (1u << 1), 14);
+        }
         if (active && my_off < w0 + 32 * M1_WIN_WORDS && my_off + my_bits > w0) {
-            WindowWriter ww{win, my_off, w0};
-            if (slice_head) {
-                // source/mpeg1_blk.c:12-20: 000001 | (vertical_pos+1)&0xff | quant_scale(5)=1 | 0
-                ww.put(1u, 24);
-                ww.put(((((uint32_t)(slice & 0xff) + 1u) & 0xffu) << 6) | (1u << 1), 14);
+            if (my_bits <= 64 && my_off >= w0 && my_off + my_bits <= w0 + 32 * M1_WIN_WORDS) {
+                const int p = my_off - w0, word = p >> 5, o = p & 31;
+                const uint32_t a = acc.hi >> o;
+                const uint32_t b = __funnelshift_r(acc.lo, acc.hi, o);
+                const uint32_t c = __funnelshift_r(0u, acc.lo, o);
+                if (a) atomicOr(&win[word], a);
+                if (b) atomicOr(&win[word + 1], b);
+                if (c) atomicOr(&win[word + 2], c);
+            } else {
+                WindowWriter ww{win, my_off, w0};           // long block, or one straddling the window
+                if (blk == 0) ww.put(3u, 2);
+                code_block(ww, rec, tid, nz, is_luma, tb);
             }
-            if (blk == 0) ww.put(3u, 2);   // address increment '1' + macroblock_type '1'
-            code_block(ww, lvl, tid, nz, is_luma, tb);
         }
         __syncthreads();
         const int nwords = min(M1_WIN_WORDS, (total_bits - w0 + 31) >> 5);
@@ -583,8 +721,8 @@ __global__ void k_synth_rgb(uint32_t seed, long first_frame, int n_frames, int W
 // -------------------------------------------------------------------------------------------
 size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
 {
-    return (size_t)16 * 16 * g.chunk_mbs + 2 * (size_t)8 * 8 * g.chunk_mbs + (size_t)threads * 128
-           + (size_t)M1_WIN_WORDS * 4 + sizeof(M1Tables) + 33 * sizeof(int) + 16;
+    (void)threads;
+    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 2) * 4 + sizeof(M1Tables) + (256 + 36) * sizeof(int) + 16;
 }
 
 int m1k_encode_threads(const M1Geom &g) { return (6 * g.chunk_mbs + 31) & ~31; }
@@ -644,9 +782,10 @@ cudaError_t m1k_launch_synth(uint32_t seed, long first_frame, int n_frames, int 
     return cudaGetLastError();
 }
 
-void m1k_fill_tables(M1Tables *t)
+void m1k_fill_tables(M1Tables *t, const M1Quant &q)
 {
     for (int i = 0; i < 112; ++i) t->ac[i] = i < M1_AC_ENTRIES ? kM1AcTable[i] : 0u;
     for (int i = 0; i < 18; ++i) t->dc[i] = kM1DcSize[i];
     for (int i = 0; i < 36; ++i) t->first[i] = i < 33 ? kM1AcFirst[i] : 0;
+    for (int z = 0; z < 64; ++z) { t->qmul[z] = q.mul[zz_raster(z)]; t->qshift[z] = q.shift[zz_raster(z)]; }
 }

@@ -108,6 +108,18 @@ class M1Encoder:
     def launches(self) -> int:
         return int(self.lib.m1cu_launch_count(self._h))
 
+    def enable_timing(self, on: bool = True):
+        self.lib.m1cu_enable_timing(self._h, int(bool(on)))
+
+    def kernel_times(self):
+        """(ms[3], launches[3]) for k_encode_chunks / k_layout / k_stitch since the last call."""
+        ms = (C.c_double * 3)()
+        n = (C.c_ulonglong * 3)()
+        rc = self.lib.m1cu_kernel_times(self._h, ms, n)
+        if rc:
+            self._err(rc)
+        return list(ms), [int(x) for x in n]
+
     def typical_out_bytes(self, n_frames: int) -> int:
         return int(self.lib.m1cu_typical_out_bytes(self._h, int(n_frames)))
 

@@ -124,6 +124,14 @@ int m1cu_synth_rgb(m1cu_ctx *ctx, uint32_t seed, long first_frame, int n_frames,
 /* counters: kernels launched by this context since creation (for bench.py's gpu_launches) */
 unsigned long long m1cu_launch_count(const m1cu_ctx *ctx);
 
+/* Per-kernel device timing for the roofline report.  While enabled, every launch of the three
+ * pipeline kernels is bracketed by CUDA events on the context's stream.  m1cu_kernel_times
+ * synchronises, adds the elapsed milliseconds of all launches recorded since the last call into
+ * ms[0..2] (0 = k_encode_chunks, 1 = k_layout, 2 = k_stitch) and their counts into n[0..2],
+ * then forgets them. */
+int m1cu_enable_timing(m1cu_ctx *ctx, int on);
+int m1cu_kernel_times(m1cu_ctx *ctx, double ms[3], unsigned long long n[3]);
+
 /* raw device/pinned memory for C callers that have no CUDA headers (the host encoder) */
 void *m1cu_device_alloc(size_t bytes);
 void  m1cu_device_free(void *p);
