@@ -81,7 +81,7 @@ bool make_quant(const int32_t qm[64], M1Quant *q)
 {
     for (int k = 0; k < 64; ++k) {
         const int m = qm[k];
-        if (m < 1 || m > 65535) return false;
+        if (m < 1 || m > 8192) return false;               // packed non-zero test needs 0x7800 - m > 0 with room
         int fl = 0;
         while ((2 << fl) <= m) ++fl;                       // floor(log2 m)
         const int S = 19 + fl;

@@ -13,7 +13,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define M1_MAX_CHUNK_MBS 40          // macroblocks per chunk (240 block-threads)
+#define M1_MAX_CHUNK_MBS 32          // macroblocks per chunk: 8*32 = 256 colour tiles, 6*32 = 192 blocks per CTA
 #define M1_BLOCK_MAX_BITS 901
 #define M1_MB_MAX_BITS (2 + 6 * M1_BLOCK_MAX_BITS)
 #define M1_SLICE_HDR_BITS 38
@@ -51,4 +51,5 @@ struct M1Tables {
     uint8_t  first[36];
     int      qmul[64];         // quantiser constants in ZIGZAG order (for the coder's dynamic index)
     int      qshift[64];
+    uint32_t ka[32], kb[32];   // per coefficient-pair word: lanes 0x7800 - m and 0x8800 - m (non-zero test)
 };

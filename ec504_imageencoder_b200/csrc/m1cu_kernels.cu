@@ -25,9 +25,21 @@ __device__ __forceinline__ int trunc_nonneg(double x)
 {
     return __double2loint(__dadd_rz(x, 4503599627370496.0));
 }
+__device__ __forceinline__ void ycbcr_from_doubles(double rd, double gd, double bd, int &y, int &cb, int &cr);
 __device__ __forceinline__ void ycbcr_exact(int r, int g, int b, int &y, int &cb, int &cr)
 {
-    const double rd = u8_to_double(r), gd = u8_to_double(g), bd = u8_to_double(b);
+    ycbcr_from_doubles(u8_to_double(r), u8_to_double(g), u8_to_double(b), y, cb, cr);
+}
+// byte B of w as a double: one I2F.F64.U8 with a byte selector (XU pipe), no extraction ALU op
+__device__ __forceinline__ double byte_to_double(uint32_t w, int b)   // b is a constant after unrolling
+{
+    double d;
+    const uint32_t s = w >> (8 * b);
+    asm("cvt.rn.f64.u8 %0, %1;" : "=d"(d) : "r"(s));
+    return d;
+}
+__device__ __forceinline__ void ycbcr_from_doubles(double rd, double gd, double bd, int &y, int &cb, int &cr)
+{
     double t = __dadd_rn(__dmul_rn(0.299, rd), __dmul_rn(0.587, gd));
     t = __dadd_rn(t, __dmul_rn(0.114, bd));
     y = trunc_nonneg(t);
@@ -76,8 +88,12 @@ __device__ __forceinline__ Fdct8 fdct_core(int x0, int x1, int x2, int x3, int x
     return o;
 }
 
-// Forward DCT of one 8x8 block held in registers: v[i*8+j] in, dct[u*8+v] out (in place).
-// Row pass source/image_processing.c:198-250, column pass :253-305.
+// Forward DCT of one 8x8 block held in registers: v[i*8+j] in, dct[u*8+v] + M1_COEF_BIAS out (in
+// place).  Row pass source/image_processing.c:198-250, column pass :253-305.  The bias (2048, folded
+// into the rounding constants of the final shifts, so it is free and exact: (a + b*2^s) >> s ==
+// (a >> s) + b) makes every output a non-negative 12-bit number, which lets two coefficients share a
+// 32-bit word without sign trouble (see the non-zero test in k_encode_chunks).
+#define M1_COEF_BIAS 2048
 __device__ __forceinline__ void fdct8x8(int (&v)[64])
 {
     const int r2 = 181;
@@ -98,14 +114,14 @@ __device__ __forceinline__ void fdct8x8(int (&v)[64])
     for (int j = 0; j < 8; ++j) {
         Fdct8 o = fdct_core(v[0 * 8 + j], v[1 * 8 + j], v[2 * 8 + j], v[3 * 8 + j],
                             v[4 * 8 + j], v[5 * 8 + j], v[6 * 8 + j], v[7 * 8 + j]);
-        v[0 * 8 + j] = (o.t0 + 16) >> 3;
-        v[4 * 8 + j] = (o.t1 + 16) >> 3;
-        v[2 * 8 + j] = (o.t2 + 16384) >> 13;
-        v[6 * 8 + j] = (o.t3 + 16384) >> 13;
-        v[7 * 8 + j] = (o.t4 - o.t5 + 16384) >> 13;
-        v[1 * 8 + j] = (o.t4 + o.t5 + 16384) >> 13;
-        v[3 * 8 + j] = ((o.t6 >> 8) * r2 + 8192) >> 12;
-        v[5 * 8 + j] = ((o.t7 >> 8) * r2 + 8192) >> 12;
+        v[0 * 8 + j] = (o.t0 + (16 + (M1_COEF_BIAS << 3))) >> 3;
+        v[4 * 8 + j] = (o.t1 + (16 + (M1_COEF_BIAS << 3))) >> 3;
+        v[2 * 8 + j] = (o.t2 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
+        v[6 * 8 + j] = (o.t3 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
+        v[7 * 8 + j] = (o.t4 - o.t5 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
+        v[1 * 8 + j] = (o.t4 + o.t5 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
+        v[3 * 8 + j] = ((o.t6 >> 8) * r2 + (8192 + (M1_COEF_BIAS << 12))) >> 12;
+        v[5 * 8 + j] = ((o.t7 >> 8) * r2 + (8192 + (M1_COEF_BIAS << 12))) >> 12;
     }
 }
 
@@ -143,10 +159,14 @@ __device__ __forceinline__ int plane_word(int blk, int r, int c)
 {
     return chunk_word(blk, r * 2 + (c >> 2)) + (c & 3);
 }
-// coefficient record of thread t: 64 shorts at byte offset t*256, 16-byte groups swizzled by t
+// Coefficient record of thread t: 32 words at byte offset t*256, each holding two BIASED
+// coefficients as 16-bit lanes: word w = (z & 15) + 16*(z >> 5) carries zigzag position z in its low
+// lane when bit 4 of z is clear, in its high lane otherwise (pairs (z, z+16)).  16-byte groups are
+// XOR-swizzled by t.  rec_index returns the index in shorts.
 __device__ __forceinline__ int rec_index(int t, int z)
 {
-    return t * 128 + ((((z >> 3) ^ t) & 7) << 3) + (z & 7);
+    const int w = (z & 15) + ((z >> 5) << 4);
+    return t * 128 + ((((w >> 2) ^ t) & 7) << 3) + ((w & 3) << 1) + ((z >> 4) & 1);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -191,8 +211,9 @@ struct WindowWriter {
 
 // quantised level of zigzag position z from the DCT coefficient c: C truncating division by the
 // scaled matrix entry (source/image_processing.c:367), as multiply-shift (see M1Tables).
-__device__ __forceinline__ int quant_level(int c, int z, const M1Tables *tb)
+__device__ __forceinline__ int quant_level(int biased, int z, const M1Tables *tb)
 {
+    const int c = biased - M1_COEF_BIAS;
     const int sh = tb->qshift[z];
     return (c * tb->qmul[z] + ((c >> 31) & ((1 << sh) - 1))) >> sh;
 }
@@ -262,7 +283,7 @@ __device__ __forceinline__ const uint8_t *px_ptr(const uint8_t *frame, const M1G
 }
 
 // byte j (0..16*CH-1) of a 16-pixel row held in w[]
-#define M1_ROW_BYTE(w, j) (((w)[(j) >> 2] >> (8 * ((j) & 3))) & 0xffu)
+#define M1_ROW_BYTE_D(w, j) byte_to_double((w)[(j) >> 2], (j) & 3)
 
 // Fast tile: 16 pixels x 2 rows of macroblock `k` of the chunk, rows 2*qy, 2*qy+1 of the
 // macroblock row; everything in range and 16-byte aligned.  128-bit loads, conversion-free FP64,
@@ -296,11 +317,11 @@ __device__ __forceinline__ void color_tile_fast(const uint8_t *__restrict__ row0
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int i = 8 * h + 4 * j + e;  // pixel 0..15 of the tile row
-                    const uint32_t R = dy ? M1_ROW_BYTE(w1, CH * i) : M1_ROW_BYTE(w0, CH * i);
-                    const uint32_t G = dy ? M1_ROW_BYTE(w1, CH * i + 1) : M1_ROW_BYTE(w0, CH * i + 1);
-                    const uint32_t B = dy ? M1_ROW_BYTE(w1, CH * i + 2) : M1_ROW_BYTE(w0, CH * i + 2);
+                    const double R = dy ? M1_ROW_BYTE_D(w1, CH * i) : M1_ROW_BYTE_D(w0, CH * i);
+                    const double G = dy ? M1_ROW_BYTE_D(w1, CH * i + 1) : M1_ROW_BYTE_D(w0, CH * i + 1);
+                    const double B = dy ? M1_ROW_BYTE_D(w1, CH * i + 2) : M1_ROW_BYTE_D(w0, CH * i + 2);
                     int cb, cr;
-                    ycbcr_exact((int)R, (int)G, (int)B, yv[e], cb, cr);
+                    ycbcr_from_doubles(R, G, B, yv[e], cb, cr);
                     if (dy == 0 && (e & 1) == 0) { sb[i >> 1] = cb; sr[i >> 1] = cr; }
                     else                         { sb[i >> 1] += cb; sr[i >> 1] += cr; }
                 }
@@ -429,23 +450,31 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
             }
         }
         fdct8x8(v);
-        // level != 0  <=>  |c| >= m  <=>  (unsigned)(c + m - 1) > 2m - 2   (m = scaled matrix entry)
-        uint32_t lo = 0, hi = 0;
+        // Pack pairs (z, z+16) of biased coefficients and test both lanes at once:
+        //   lane + (0x7800 - m) has bit 15 set  <=>  c >=  m
+        //   (0x8800 - m) - lane has bit 15 set  <=>  c <= -m          (m = scaled matrix entry, no
+        // carries cross the lanes: every lane value stays inside [0, 0xffff]), so level != 0 <=> either.
+        // Shifting the accumulator right once per word lands word i's flags on bits i and 16+i.
+        uint32_t pk[32];
+        uint32_t half[2];
 #pragma unroll
-        for (int z = 0; z < 32; ++z) { const int k = zz_raster(z); if ((unsigned)(v[k] + q.ta[k]) > (unsigned)q.tb[k]) lo |= 1u << z; }
+        for (int hblk = 0; hblk < 2; ++hblk) {
+            uint32_t acc = 0;
 #pragma unroll
-        for (int z = 32; z < 64; ++z) { const int k = zz_raster(z); if ((unsigned)(v[k] + q.ta[k]) > (unsigned)q.tb[k]) hi |= 1u << (z - 32); }
-        nz = ((unsigned long long)hi << 32) | lo;
-        // coefficient record: zigzag order (source/image_processing.c:373-381), int16 (|c| <= 2042)
-#pragma unroll
-        for (int cidx = 0; cidx < 8; ++cidx) {
-            uint4 w;
-            w.x = __byte_perm(v[zz_raster(cidx * 8 + 0)], v[zz_raster(cidx * 8 + 1)], 0x5410);
-            w.y = __byte_perm(v[zz_raster(cidx * 8 + 2)], v[zz_raster(cidx * 8 + 3)], 0x5410);
-            w.z = __byte_perm(v[zz_raster(cidx * 8 + 4)], v[zz_raster(cidx * 8 + 5)], 0x5410);
-            w.w = __byte_perm(v[zz_raster(cidx * 8 + 6)], v[zz_raster(cidx * 8 + 7)], 0x5410);
-            *(uint4 *)(rec + tid * 128 + (((cidx ^ tid) & 7) << 3)) = w;
+            for (int i = 0; i < 16; ++i) {
+                const int w = hblk * 16 + i, z = hblk * 32 + i;
+                const uint32_t p = (uint32_t)v[zz_raster(z)] | ((uint32_t)v[zz_raster(z + 16)] << 16);
+                pk[w] = p;
+                const uint32_t f = ((p + tb->ka[w]) | (tb->kb[w] - p)) & 0x80008000u;
+                acc = f + (acc >> 1);
+            }
+            half[hblk] = acc;
         }
+        nz = ((unsigned long long)half[1] << 32) | half[0];
+#pragma unroll
+        for (int gI = 0; gI < 8; ++gI)
+            *(uint4 *)(rec + tid * 128 + (((gI ^ tid) & 7) << 3)) =
+                make_uint4(pk[4 * gI], pk[4 * gI + 1], pk[4 * gI + 2], pk[4 * gI + 3]);
     }
 
     // ---- phase 3: code every block into registers, scan the lengths in coding order ----------
@@ -725,7 +754,7 @@ size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
     return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 2) * 4 + sizeof(M1Tables) + (256 + 36) * sizeof(int) + 16;
 }
 
-int m1k_encode_threads(const M1Geom &g) { return (6 * g.chunk_mbs + 31) & ~31; }
+int m1k_encode_threads(const M1Geom &g) { return (8 * g.chunk_mbs + 31) & ~31; }   // one colour tile per thread; 6C of them own a block
 
 cudaError_t m1k_prepare(const M1Geom &g)
 {
@@ -788,4 +817,10 @@ void m1k_fill_tables(M1Tables *t, const M1Quant &q)
     for (int i = 0; i < 18; ++i) t->dc[i] = kM1DcSize[i];
     for (int i = 0; i < 36; ++i) t->first[i] = i < 33 ? kM1AcFirst[i] : 0;
     for (int z = 0; z < 64; ++z) { t->qmul[z] = q.mul[zz_raster(z)]; t->qshift[z] = q.shift[zz_raster(z)]; }
+    for (int w = 0; w < 32; ++w) {
+        const int zlo = (w & 15) + ((w >> 4) << 5), zhi = zlo + 16;
+        const uint32_t mlo = (uint32_t)q.ta[zz_raster(zlo)] + 1u, mhi = (uint32_t)q.ta[zz_raster(zhi)] + 1u;
+        t->ka[w] = ((0x7800u - mhi) << 16) | (0x7800u - mlo);
+        t->kb[w] = ((0x8800u - mhi) << 16) | (0x8800u - mlo);
+    }
 }
