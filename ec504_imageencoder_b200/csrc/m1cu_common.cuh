@@ -17,7 +17,7 @@
 #define M1_BLOCK_MAX_BITS 901
 #define M1_MB_MAX_BITS (2 + 6 * M1_BLOCK_MAX_BITS)
 #define M1_SLICE_HDR_BITS 38
-#define M1_WIN_WORDS 1024            // shared-memory bit window per chunk pass (4 KiB = 32768 bits)
+#define M1_WIN_WORDS 512             // shared-memory bit window per chunk pass (2 KiB = 16384 bits)
 
 enum { M1_ERRBIT_CAPACITY = 1, M1_ERRBIT_LEVEL = 2 };
 

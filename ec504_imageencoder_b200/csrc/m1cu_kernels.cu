@@ -147,8 +147,8 @@ __host__ __device__ constexpr int zz_raster(int z)
 // per block, 128-bit loads) are bank-conflict free.
 //   luma blocks:   blk = by * 2C + bc      (by = block row 0/1 of the macroblock row, bc = 8-pixel column)
 //   chroma blocks: blk = 4C + mb (Cb), 5C + mb (Cr)                       C = chunk_mbs
-// Consumer thread t handles block t.  After a thread has pulled its block into registers it
-// reuses the first 128 bytes of the same 256 bytes for its DCT-coefficient record (int16, zigzag).
+// Exactly one consumer thread reads each block.  After it has pulled the block into registers it
+// reuses the first 128 bytes of the same 256 bytes for the block's DCT-coefficient record.
 // -------------------------------------------------------------------------------------------
 __device__ __forceinline__ int blk_key(int blk) { return (blk ^ (blk >> 3)) & 7; }
 __device__ __forceinline__ int chunk_word(int blk, int i)      // first word of chunk i of block blk
@@ -383,10 +383,10 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
     short *rec = (short *)smem;                                  // aliases planes (see layout note)
     uint32_t *win = (uint32_t *)(planes + 6 * C * 64);           // [M1_WIN_WORDS + 2]
     M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS + 2);
-    int *lens = (int *)(tb + 1);                                 // [256] bits per coding position
-    int *scan = lens + 256;                                      // [32] warp totals, [32] chunk total
+    int *wtot = (int *)(tb + 1);                                 // [8] bits per warp
 
     for (int i = tid; i < (int)(sizeof(M1Tables) / 4); i += nthr) ((uint32_t *)tb)[i] = ((const uint32_t *)gtab)[i];
+    for (int i = tid; i < M1_WIN_WORDS + 2; i += nthr) win[i] = 0;
 
     const uint8_t *fr = rgb + (size_t)frame * g.frame_stride;
 
@@ -427,19 +427,19 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
     }
     __syncthreads();
 
-    // ---- phase 2: one thread per 8x8 block (thread t = plane block t): DCT, non-zero mask ---------
-    int mb, blk;                                            // macroblock in chunk, block 0..5 in coding order
-    if (tid < 4 * C) { const int by = tid >= 2 * C, bc = tid - by * 2 * C; mb = bc >> 1; blk = by * 2 + (bc & 1); }
-    else             { const int cr = tid >= 5 * C; mb = tid - (4 + cr) * C; blk = 4 + cr; }
-    const bool active = tid < 6 * C && mb < nmb;
+    // ---- phase 2: one thread per 8x8 block, threads in CODING order (t = 6*mb + blk), so the
+    // bit offsets are a plain scan over the thread index.  pb = the thread's plane block.
+    const int mb = tid / 6, blk = tid - mb * 6;             // macroblock in chunk, block 0..5
+    const bool active = mb < nmb;
     const bool is_luma = blk < 4;
-    const int pos = mb * 6 + blk;                           // coding position within the chunk
+    const int pb = is_luma ? (blk >> 1) * 2 * C + 2 * mb + (blk & 1) : blk * C + mb;
     unsigned long long nz = 0;
+    BitAcc acc{0u, 0u, 0};
     if (active) {
         int v[64];
         {
-            const int key4 = blk_key(tid) << 2;
-            const int *src = planes + tid * 64;
+            const int key4 = blk_key(pb) << 2;
+            const int *src = planes + pb * 64;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int o = ((i << 2) ^ key4);
@@ -459,33 +459,39 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
         uint32_t half[2];
 #pragma unroll
         for (int hblk = 0; hblk < 2; ++hblk) {
-            uint32_t acc = 0;
+            uint32_t fl = 0;
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const int w = hblk * 16 + i, z = hblk * 32 + i;
                 const uint32_t p = (uint32_t)v[zz_raster(z)] | ((uint32_t)v[zz_raster(z + 16)] << 16);
                 pk[w] = p;
                 const uint32_t f = ((p + tb->ka[w]) | (tb->kb[w] - p)) & 0x80008000u;
-                acc = f + (acc >> 1);
+                fl = f + (fl >> 1);
             }
-            half[hblk] = acc;
+            half[hblk] = fl;
         }
         nz = ((unsigned long long)half[1] << 32) | half[0];
+        // the block's samples are in registers now: its 256 bytes of plane become the record
 #pragma unroll
         for (int gI = 0; gI < 8; ++gI)
-            *(uint4 *)(rec + tid * 128 + (((gI ^ tid) & 7) << 3)) =
+            *(uint4 *)(rec + pb * 128 + (((gI ^ pb) & 7) << 3)) =
                 make_uint4(pk[4 * gI], pk[4 * gI + 1], pk[4 * gI + 2], pk[4 * gI + 3]);
+
+        // ---- phase 3: code the block into registers ------------------------------------------
+        if (blk == 0) acc.put(3u, 2);                       // address increment '1' + macroblock_type '1'
+        if (code_block(acc, rec, pb, nz, is_luma, tb)) atomicOr(err, M1_ERRBIT_LEVEL);
     }
 
-    // ---- phase 3: code every block into registers, scan the lengths in coding order ----------
-    BitAcc acc{0u, 0u, 0};
-    int bad = 0;
-    if (active) {
-        if (blk == 0) acc.put(3u, 2);                       // address increment '1' + macroblock_type '1'
-        bad = code_block(acc, rec, tid, nz, is_luma, tb);
-        lens[pos] = acc.n;
+    // scan of the block lengths in thread (= coding) order
+    const int lane = tid & 31, warp = tid >> 5;
+    const int my_bits = acc.n;
+    int incl = my_bits;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
     }
-    if (bad) atomicOr(err, M1_ERRBIT_LEVEL);
+    if (lane == 31) wtot[warp] = incl;
     __syncthreads();
 
     if (kLevels) {
@@ -493,47 +499,22 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
         short *dst = levels + ((size_t)frame * g.mbs_per_frame + (size_t)slice * g.mbs_per_slice + mb0) * 384;
         for (int i = tid; i < nmb * 384; i += nthr) {
             const int p = i >> 6, z = i & 63, m = p / 6, b = p - m * 6;
-            const int t = b < 4 ? (b >> 1) * 2 * C + 2 * m + (b & 1) : (b == 4 ? 4 * C + m : 5 * C + m);
+            const int t = b < 4 ? (b >> 1) * 2 * C + 2 * m + (b & 1) : b * C + m;
             dst[i] = (short)quant_level(rec[rec_index(t, z)], z, tb);
         }
     }
 
-    const int lane = tid & 31, warp = tid >> 5;
-    const int npos = 6 * nmb;
-    const int mine = tid < npos ? lens[tid] : 0;            // thread i scans coding position i
-    int incl = mine;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
-    if (lane == 31) scan[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        const int nw = (nthr + 31) >> 5;
-        const int w = lane < nw ? scan[lane] : 0;
-        int wi = w;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, wi, d);
-            if (lane >= d) wi += t;
-        }
-        if (lane < nw) scan[lane] = wi - w;
-        if (lane == 31) scan[32] = wi;
-    }
-    __syncthreads();
     const int hdr_bits = chunk == 0 ? M1_SLICE_HDR_BITS : 0;
-    if (tid < npos) lens[tid] = hdr_bits + scan[warp] + incl - mine;   // exclusive offset of position tid
-    const int total_bits = hdr_bits + scan[32];
-    __syncthreads();
-    const int my_off = active ? lens[pos] : 0;
-    const int my_bits = acc.n;
+    int base = hdr_bits, total_bits = hdr_bits;
+    {
+        const int nw = nthr >> 5;
+        for (int w = 0; w < nw; ++w) { const int t = wtot[w]; total_bits += t; if (w < warp) base += t; }
+    }
+    const int my_off = base + incl - my_bits;
 
     uint32_t *out = staging + ((size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk)
                                   * (g.chunk_stride / 4);
-    for (int w0 = 0; w0 < total_bits; w0 += 32 * M1_WIN_WORDS) {
-        for (int i = tid; i < M1_WIN_WORDS + 2; i += nthr) win[i] = 0;
-        __syncthreads();
+    for (int w0 = 0;; w0 += 32 * M1_WIN_WORDS) {            // the window was zeroed at kernel start
         if (tid == 0 && hdr_bits && w0 == 0) {
             // source/mpeg1_blk.c:12-20: 000001 | (vertical_pos+1)&0xff | quant_scale(5)=1 | 0
             WindowWriter ww{win, 0, 0};
@@ -552,12 +533,15 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
             } else {
                 WindowWriter ww{win, my_off, w0};           // long block, or one straddling the window
                 if (blk == 0) ww.put(3u, 2);
-                code_block(ww, rec, tid, nz, is_luma, tb);
+                code_block(ww, rec, pb, nz, is_luma, tb);
             }
         }
         __syncthreads();
         const int nwords = min(M1_WIN_WORDS, (total_bits - w0 + 31) >> 5);
         for (int i = tid; i < nwords; i += nthr) out[(w0 >> 5) + i] = win[i];
+        if (w0 + 32 * M1_WIN_WORDS >= total_bits) break;
+        __syncthreads();                                    // rare: the chunk needs another window pass
+        for (int i = tid; i < M1_WIN_WORDS + 2; i += nthr) win[i] = 0;
         __syncthreads();
     }
     if (tid == 0)
@@ -751,7 +735,7 @@ __global__ void k_synth_rgb(uint32_t seed, long first_frame, int n_frames, int W
 size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
 {
     (void)threads;
-    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 2) * 4 + sizeof(M1Tables) + (256 + 36) * sizeof(int) + 16;
+    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 2) * 4 + sizeof(M1Tables) + 8 * sizeof(int) + 16;
 }
 
 int m1k_encode_threads(const M1Geom &g) { return (8 * g.chunk_mbs + 31) & ~31; }   // one colour tile per thread; 6C of them own a block
