@@ -688,7 +688,7 @@ k_stitch(const __grid_constant__ M1Geom g, const uint32_t *__restrict__ staging,
 
 // -------------------------------------------------------------------------------------------
 // Full-resolution planes (the .bit side files, source/image_processing.c:753-787) and the
-// synthetic generator (same integer formula as oracle/m1_oracle.c:m1o_synth_rgb).
+// synthetic generator (the test oracle restates the same integer formula).
 // -------------------------------------------------------------------------------------------
 __global__ void k_ycbcr_planes(const uint8_t *__restrict__ rgb, int channels, size_t npix,
                                uint8_t *__restrict__ Y, uint8_t *__restrict__ Cb, uint8_t *__restrict__ Cr)
