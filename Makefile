@@ -1,0 +1,58 @@
+# Top-level build.  Target names follow the reference's Makefile (all / sharedlib / jni / clean);
+# `cuda` and `oracle` are ours.
+#
+#   make cuda       ec504_imageencoder_b200/libm1cu.so      CUDA kernels + C ABI (nvcc, sm_100a)
+#   make sharedlib  ec504_imageencoder_b200/libencoder.so   host C: reference API + driver (gcc), links libm1cu
+#                   ./libencoder.so                         symlink, where the reference's target puts it
+#   make all        ./encoder                               main.c + libencoder
+#   make jni        ./libencoder_jni.so                     needs JAVA_HOME with <jni.h>
+#   make oracle     oracle/libm1oracle.so (+ oracle/_ref when the reference checkout is present)
+
+CC      ?= gcc
+NVCC    ?= nvcc
+PKG     := ec504_imageencoder_b200
+HOST    := $(PKG)/csrc/host
+OBJDIR  := $(HOST)/_build
+CFLAGS  := -O2 -g -fPIC -Iinclude -ffp-contract=off -Wall -Wno-unused-result
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared
+HOSTSRC := m1_bitvector.c m1_stream.c m1_vlc.c m1_blk.c m1_stages.c m1_driver.c m1_stb_stub.c
+HOSTOBJ := $(addprefix $(OBJDIR)/,$(HOSTSRC:.c=.o))
+# stb_image v2.30 (public domain): compiled from the copy the reference vendors, or from STB_IMAGE_H
+STB_IMAGE_H ?= /root/reference/include/stb_image.h
+STBOBJ  := $(OBJDIR)/stb_image.o
+
+.PHONY: all sharedlib jni cuda oracle clean
+all: encoder
+
+cuda: $(PKG)/libm1cu.so
+$(PKG)/libm1cu.so: $(PKG)/csrc/m1cu_kernels.cu $(PKG)/csrc/m1cu_api.cu $(wildcard $(PKG)/csrc/*.h $(PKG)/csrc/*.cuh) include/m1cu.h
+	$(NVCC) $(NVFLAGS) -o $@ $(PKG)/csrc/m1cu_kernels.cu $(PKG)/csrc/m1cu_api.cu
+
+$(OBJDIR)/%.o: $(HOST)/%.c $(wildcard include/*.h) $(HOST)/m1_vlc_data.inc
+	@mkdir -p $(OBJDIR)
+	$(CC) $(CFLAGS) -c $< -o $@
+
+ifneq ($(wildcard $(STB_IMAGE_H)),)
+$(STBOBJ): $(STB_IMAGE_H)
+	@mkdir -p $(OBJDIR)
+	$(CC) -O2 -fPIC -w -x c -DSTB_IMAGE_IMPLEMENTATION -c $(STB_IMAGE_H) -o $@
+endif
+STBLINK := $(if $(wildcard $(STB_IMAGE_H))$(wildcard $(STBOBJ)),$(STBOBJ),)
+
+sharedlib: $(PKG)/libencoder.so
+$(PKG)/libencoder.so: $(HOSTOBJ) $(STBLINK) $(PKG)/libm1cu.so
+	$(CC) -shared -o $@ $(HOSTOBJ) $(STBLINK) -L$(PKG) -lm1cu -Wl,-rpath,'$$ORIGIN' -lm
+	ln -sf $(PKG)/libencoder.so libencoder.so
+
+encoder: main.c $(PKG)/libencoder.so
+	$(CC) $(CFLAGS) -o $@ main.c -L$(PKG) -lencoder -lm1cu -Wl,-rpath,'$$ORIGIN/$(PKG)' -lm
+
+jni: encoder_jni.c $(PKG)/libencoder.so
+	$(CC) $(CFLAGS) -I$(JAVA_HOME)/include -I$(JAVA_HOME)/include/linux -I$(JAVA_HOME)/include/darwin -shared \
+	    -o libencoder_jni.so encoder_jni.c -L$(PKG) -lencoder -lm1cu -Wl,-rpath,'$$ORIGIN/$(PKG)' -lm
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf $(OBJDIR) encoder libencoder.so libencoder_jni.so $(PKG)/libencoder.so

@@ -1,0 +1,193 @@
+"""libencoder.so: the host-C side of the boundary.
+
+CPU part: the per-stage compatibility functions (reference `make sharedlib` API) against the
+oracle and the golden vectors.  GPU part: the driver (GPU hot path + host headers) against the
+oracle's stream and the reference binary's own output file."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLD = os.path.join(HERE, "golden")
+
+REF_EXPORTS_HOT = """VLC_encode bitvector_clone bitvector_concat bitvector_expand_size bitvector_fwrite bitvector_init
+bitvector_new bitvector_pos bitvector_print bitvector_put_binstring bitvector_put_bit bitvector_put_byte
+bitvector_put_byte_ent bitvector_put_byte_off bitvector_toarray check_dimensions convert_rgb_to_ycbcr display_u8arr
+encode_blk_coeff encode_block_end encode_block_header_i encode_coeff_sz_fast encode_macblk_address_value
+encode_macblk_encoding_value encode_macroblock_end encode_macroblock_header_i equalize_coefficients extract_8x8_block
+fast_DCT mpeg1_file_header mpeg1_gop mpeg1_packet_header mpeg1_picture_header mpeg1_sequence_end mpeg1_sequence_header
+mpeg1_slice mpeg1_sys_header print_array quantization run_length_encode scale_quantization_matrix subsampling_420
+write_to_bitstream zigzag_scanning mpeg_encode_procedure
+Q_MATRIX ZIGZAG_ORDER START_FILE START_PICTURE blk_coeff_1_f blk_coeff_1_n blk_coeff_end blk_rle_lookup blk_rle_table
+dc_sz_chroma_table dc_sz_luma_table encoding_table mv_encoding_table slice_start_code""".split()
+
+
+@pytest.fixture(scope="module")
+def host():
+    import subprocess
+    root = os.path.dirname(HERE)
+    from ec504_imageencoder_b200 import _native, hostlib
+    _native.build_cuda()
+    subprocess.run(["make", "-s", "-C", root, "sharedlib"], check=True)
+    return hostlib
+
+
+def test_exports(host):
+    L = host.lib()
+    for name in REF_EXPORTS_HOT:
+        assert hasattr(L, name), name
+
+
+def _block_bits(host, zz, luma):
+    L = host.lib()
+    z = (C.c_int * 64)(*[int(v) for v in zz])
+    eq = (C.c_int * 64)()
+    rle = (C.c_int * 132)()
+    L.equalize_coefficients(z, eq)
+    L.run_length_encode(eq, rle)
+    bv = L.bitvector_new(b"", 8)
+    L.encode_block_header_i(luma, rle, bv)
+    L.encode_block_end(bv)
+    return bv.contents.bitstring()
+
+
+def test_block_syntax_against_golden(host, port):
+    with open(os.path.join(GOLD, "kat.json")) as f:
+        kat = json.load(f)
+    n = 0
+    for b in kat["blocks"]:
+        if b["bits"] is None:
+            continue
+        assert _block_bits(host, b["zz"], b["luma"]) == b["bits"]
+        n += 1
+    assert n > 600
+    L = host.lib()
+    bv = L.bitvector_new(b"", 8)
+    L.mpeg1_slice(1, 0, bv)
+    L.encode_macroblock_header_i(1, 1, bv)
+    assert bv.contents.bitstring() == kat["slice_header_bits"]["0"]
+    bv = L.bitvector_new(b"", 8)
+    L.encode_macroblock_header_i(70, 1, bv)          # two escapes + increment 4 + type
+    assert bv.contents.bitstring() == "00000001000" * 2 + "0011" + "1"
+
+
+def test_stage_functions_against_oracle(host, port):
+    L = host.lib()
+    rng = np.random.default_rng(11)
+    for q in (1, 12, 50, 89, 100):
+        m = (C.c_int * 64)()
+        L.scale_quantization_matrix(m, q)
+        assert list(m) == port.qmatrix(q).tolist()
+    for i in range(300):
+        blk = rng.integers(0, 256, 64, dtype=np.uint8) if i % 2 else (rng.integers(0, 2, 64) * 255).astype(np.uint8)
+        d = (C.c_double * 64)()
+        L.fast_DCT(blk.ctypes.data, d)
+        want = port.fdct8x8(blk)
+        assert [int(x) for x in d] == want.tolist()
+        q = (5, 12, 50)[i % 3]
+        qi, zz = (C.c_int * 64)(), (C.c_int * 64)()
+        L.quantization(d, qi, q)
+        L.zigzag_scanning(qi, zz)
+        assert list(zz) == port.quant_zigzag(want, port.qmatrix(q)).tolist()
+    # extract_8x8_block
+    plane = rng.integers(0, 256, (40, 64), dtype=np.uint8)
+    out = np.zeros((8, 8), np.uint8)
+    L.extract_8x8_block(plane.ctypes.data, 64, 24, 16, out.ctypes.data)
+    assert np.array_equal(out, plane[16:24, 24:32])
+
+
+def test_headers_against_golden(host):
+    with open(os.path.join(GOLD, "kat.json")) as f:
+        kat = json.load(f)
+    L = host.lib()
+    buf = np.zeros(27, np.uint8)
+    L.mpeg1_file_header(2202035, buf.ctypes.data)
+    L.mpeg1_sys_header(2202035, 0xE6, buf[12:].ctypes.data)
+    assert buf.tobytes().hex() == kat["file_prologue"]
+    for p in kat["frame_prefix"]:
+        hour = p["i"] & 0xFF
+        out = np.zeros(44, np.uint8)
+        L.mpeg1_packet_header(1 + 3600 * hour, out.ctypes.data)
+        W, H = (p["W"] & 0xFF, p["H"] & 0xFF) if p["mode"] == 1 else (p["W"], p["H"])
+        L.mpeg1_sequence_header(W, H, 1, 4, 3, out[16:].ctypes.data)
+        L.mpeg1_gop(0, hour, 0, 0, 0, 1, 0, out[28:].ctypes.data)
+        bid = np.zeros(4, np.uint8)
+        L.mpeg1_picture_header(0, 1, 0xFFFF, bid.ctypes.data, out[36:].ctypes.data)
+        fwd = (44 + p["payload"] - 8) & 0xFFFF
+        out[4], out[5] = fwd >> 8, fwd & 0xFF
+        assert out.tobytes().hex() == p["hex"], p
+    end = np.zeros(4, np.uint8)
+    L.mpeg1_sequence_end(end.ctypes.data)
+    assert end.tobytes() == b"\x00\x00\x01\xb7"
+
+
+def test_bitvector_semantics(host):
+    L = host.lib()
+    bv = L.bitvector_new(b"101", 3)                  # size is a capacity hint, length = strlen
+    assert bv.contents.cap == 3 and bv.contents.bitstring() == "101"
+    L.bitvector_put_byte_off(bv, 0b00010110, 5, 3)   # low five bits
+    assert bv.contents.bitstring() == "101" + "10110"
+    L.bitvector_put_byte(bv, bytes([0b11000000]), 2)          # top two bits
+    L.bitvector_put_byte_ent(bv, bytes([0x0F]))
+    assert bv.contents.bitstring() == "10110110" + "11" + "00001111"
+    other = L.bitvector_new(b"0011", 8)
+    L.bitvector_concat(bv, other)
+    assert bv.contents.bitstring().endswith("00001111" + "0011") and bv.contents.cap == 22
+    cl = L.bitvector_clone(bv)
+    assert cl.contents.bitstring() == bv.contents.bitstring() and cl.contents.cursor == 22
+    for run, level, want in ((2, 2, "000110"), (1, 1, "11"), (1, 2, "00101"), (2, 40, "00000100000100101000")):
+        assert L.encode_blk_coeff(run, level, 0).contents.bitstring() == want
+    assert not L.encode_blk_coeff(1, 256, 0)         # NULL, as the reference (source/vlc.c:383)
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU part
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_driver_stream_equals_oracle(host, port):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    for (W, H, n, q, mode, kind) in ((352, 240, 5, 12, 0, 0), (100, 70, 3, 50, 0, 1), (400, 600, 3, 12, 1, 1)):
+        frames = np.stack([port.synth_rgb(77, f, W, H, kind) for f in range(n)])
+        assert host.encode_frames_to_memory(frames, q, mode) == port.encode_stream(frames, q, mode)
+
+
+@pytest.mark.gpu
+def test_driver_on_reference_fixture(host, port, tmp_path):
+    """REF_COMPAT end to end through the C driver entry point: the stream equals the file the
+    reference's own binary wrote for images.zip, except the 4 uninitialised bytes per frame."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from test_oracle_golden import masked_equal
+    z = np.load(os.path.join(GOLD, "refcompat_inputs.npz"))
+    ref_video = open(os.path.join(GOLD, "refcompat_video.mpeg"), "rb").read()
+    images, frame_image = z["images"], z["frame_image"]
+    frames = np.zeros((len(frame_image), 600, 400, 3), np.uint8)       # rows >= 144 are never read in REF_COMPAT
+    for i, idx in enumerate(frame_image):
+        frames[i, :144] = images[int(idx)]
+    ours = host.encode_frames_to_memory(frames, 12, 1)
+    sizes = [len(port.encode_picture(images[int(i)], 12, 1)) for i in frame_image]
+    assert masked_equal(ours, ref_video, 30, sizes)
+    path = str(tmp_path / "v.mpeg")
+    assert host.lib().m1_encode_frames_to_file(path.encode(), frames.ctypes.data, 30, 400, 600, 3, 12, 1) == 0
+    assert open(path, "rb").read() == ours
+
+
+@pytest.mark.gpu
+def test_mpeg_encode_procedure_return_codes(host, tmp_path):
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    # unwritable output -> 1 (reference include/encoder.h:77-80)
+    assert host.mpeg_encode_procedure(str(tmp_path / "imgs"), str(tmp_path / "bs"), str(tmp_path / "nodir" / "v.mpeg")) == 1
+    # missing images folder -> created, 0 (:111-116); prologue already written (27 bytes)
+    v = tmp_path / "v.mpeg"
+    assert host.mpeg_encode_procedure(str(tmp_path / "imgs"), str(tmp_path / "bs"), str(v)) == 0
+    assert (tmp_path / "imgs").is_dir() and (tmp_path / "bs").is_dir() and v.stat().st_size == 27
+    # empty images folder -> -1 (:175-183)
+    assert host.mpeg_encode_procedure(str(tmp_path / "imgs"), str(tmp_path / "bs"), str(v)) == -1
