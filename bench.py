@@ -177,32 +177,12 @@ def _port_fps(nframes):
 # --------------------------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------------------------
-def gather_to_rank0(dist, rank, world, res, n_frames, recv_buf, torch):
-    """north_star (e): per-frame byte counts + compressed segments to rank 0 over NCCL.
-    all_gather of the (tiny) size vectors, then grouped send/recv of each rank's segment."""
-    sizes = [torch.empty(n_frames, dtype=torch.int32, device=res.frame_bytes.device) for _ in range(world)]
-    dist.all_gather(sizes, res.frame_bytes)
-    ends = torch.empty(world, dtype=torch.int64, device=res.frame_bytes.device)
-    dist.all_gather_into_tensor(ends, res.frame_offsets[-1:].contiguous())
-    ends_h = ends.cpu().tolist()                        # one small D2H: recv sizes must be known on the host
-    ops, pos = [], 0
-    if rank == 0:
-        for r in range(1, world):
-            ops.append(dist.P2POp(dist.irecv, recv_buf[pos:pos + ends_h[r]], r))
-            pos += ends_h[r]
-    else:
-        ops.append(dist.P2POp(dist.isend, res.out[:ends_h[rank]], 0))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    return sizes, ends_h
-
-
 def run_ours(args):
     import numpy as np
     import torch
     import torch.distributed as dist
     from ec504_imageencoder_b200 import M1Encoder, MODE_FULL, SYNTH_NATURAL
+    from ec504_imageencoder_b200.distributed import gather_to_rank0
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -230,7 +210,7 @@ def run_ours(args):
         def step():
             enc.encode_device(rgb, res=res, check=False)
             if world > 1:
-                gather_to_rank0(dist, rank, world, res, n, recv_buf, torch)
+                gather_to_rank0(res.out, res.frame_bytes, res.frame_offsets, [n] * world, recv=recv_buf)
 
         def fence():
             if world > 1:
