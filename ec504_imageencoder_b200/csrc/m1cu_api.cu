@@ -180,7 +180,12 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     g.W = width; g.H = height; g.channels = channels; g.mode = mode;
     if (mode == M1CU_MODE_FULL) { g.slices = (height + 15) / 16; g.mbs_per_slice = (width + 15) / 16; }
     else                        { g.slices = 6; g.mbs_per_slice = 9; }
-    g.chunks_per_slice = (g.mbs_per_slice + M1_MAX_CHUNK_MBS - 1) / M1_MAX_CHUNK_MBS;
+    int max_chunk = M1_DEFAULT_CHUNK_MBS;
+    if (const char *v = getenv("M1_CHUNK_MBS")) {          // tuning knob (1..M1_MAX_CHUNK_MBS)
+        const int c = atoi(v);
+        if (c >= 1 && c <= M1_MAX_CHUNK_MBS) max_chunk = c;
+    }
+    g.chunks_per_slice = (g.mbs_per_slice + max_chunk - 1) / max_chunk;
     g.chunk_mbs = (g.mbs_per_slice + g.chunks_per_slice - 1) / g.chunks_per_slice;
     g.chunks_per_slice = (g.mbs_per_slice + g.chunk_mbs - 1) / g.chunk_mbs;
     g.chunks_per_frame = g.chunks_per_slice * g.slices;
@@ -189,6 +194,7 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     g.frame_stride = (unsigned long long)width * height * channels;
     // 128-bit tile loads need 16-pixel tiles to start on 16-byte boundaries in every row and picture
     g.fast_load = (mode == M1CU_MODE_FULL && (channels == 3 || channels == 4) && width % 16 == 0) ? channels : 0;
+    g.debug_skip = getenv("M1_DEBUG_SKIP") ? atoi(getenv("M1_DEBUG_SKIP")) : 0;
 
     m1cu_qmatrix(quality, ctx->qm);
     if (!make_quant(ctx->qm, &ctx->q)) { delete ctx; return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: quantiser constants failed self-check"); }

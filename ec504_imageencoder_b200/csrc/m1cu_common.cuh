@@ -13,7 +13,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#define M1_MAX_CHUNK_MBS 32          // macroblocks per chunk: 8*32 = 256 colour tiles, 6*32 = 192 blocks per CTA
+#define M1_MAX_CHUNK_MBS 16          // upper bound of macroblocks per chunk (CTA of 128 threads)
+#define M1_DEFAULT_CHUNK_MBS 16      // default target: 8*16 = 128 colour-tile threads, 6*16 = 96 block threads per CTA
 #define M1_BLOCK_MAX_BITS 901
 #define M1_MB_MAX_BITS (2 + 6 * M1_BLOCK_MAX_BITS)
 #define M1_SLICE_HDR_BITS 38
@@ -25,6 +26,7 @@ struct M1Geom {
     int W, H, channels;
     int mode;                  // M1CU_MODE_*
     int fast_load;             // 3 / 4: channels with 16-byte-aligned 16-pixel tiles, 0: generic loads only
+    int debug_skip;            // profiling only (env M1_DEBUG_SKIP): bit 0 skips the colour phase, bit 1 the block phases
     int slices;                // per picture
     int mbs_per_slice;
     int chunk_mbs;             // macroblocks per chunk (last chunk of a slice may hold fewer)

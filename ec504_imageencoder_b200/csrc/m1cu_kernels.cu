@@ -163,10 +163,13 @@ __device__ __forceinline__ int plane_word(int blk, int r, int c)
 // coefficients as 16-bit lanes: word w = (z & 15) + 16*(z >> 5) carries zigzag position z in its low
 // lane when bit 4 of z is clear, in its high lane otherwise (pairs (z, z+16)).  16-byte groups are
 // XOR-swizzled by t.  rec_index returns the index in shorts.
+// kStride = distance between records in shorts (128 when the record aliases the block's plane
+// memory, 64 for the dense record array of the warp-specialised kernel).
+template <int kStride = 128>
 __device__ __forceinline__ int rec_index(int t, int z)
 {
     const int w = (z & 15) + ((z >> 5) << 4);
-    return t * 128 + ((((w >> 2) ^ t) & 7) << 3) + ((w & 3) << 1) + ((z >> 4) & 1);
+    return t * kStride + ((((w >> 2) ^ t) & 7) << 3) + ((w & 3) << 1) + ((z >> 4) & 1);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -222,7 +225,7 @@ __device__ __forceinline__ int quant_level(int biased, int z, const M1Tables *tb
 // source/vlc.c:315-385), end of block (source/mpeg1_blk.c:115-117).  rec: the shared coefficient
 // records; nz: bit z set <=> quantised level z is non-zero.  Returns non-zero when a coded AC
 // level is outside the reference's encodable range.
-template <class Sink>
+template <int kStride = 128, class Sink>
 __device__ __forceinline__ int code_block(Sink &s, const short *rec, int tid, unsigned long long nz,
                                           bool is_luma, const M1Tables *tb)
 {
@@ -230,7 +233,7 @@ __device__ __forceinline__ int code_block(Sink &s, const short *rec, int tid, un
     int prev = -1;
     unsigned long long m = nz;
     if (nz & 1ull) {
-        const int v = quant_level(rec[rec_index(tid, 0)], 0, tb);
+        const int v = quant_level(rec[rec_index<kStride>(tid, 0)], 0, tb);
         int c = v < 0 ? -v : v;
         const int low = c & 0xff;
         const int sz = low ? 32 - __clz(low) : 1;            // highest set bit of bits 0..7, default 1
@@ -249,7 +252,7 @@ __device__ __forceinline__ int code_block(Sink &s, const short *rec, int tid, un
     while (m) {
         const int k = __ffsll((long long)m) - 1;
         m &= m - 1ull;
-        const int L = quant_level(rec[rec_index(tid, k)], k, tb);
+        const int L = quant_level(rec[rec_index<kStride>(tid, k)], k, tb);
         const int r = k - prev - 2;                          // run - 1 of source/vlc.c:326
         const int mag = L < 0 ? -L : L;
         const int a = mag - 1;
@@ -285,65 +288,82 @@ __device__ __forceinline__ const uint8_t *px_ptr(const uint8_t *frame, const M1G
 // byte j (0..16*CH-1) of a 16-pixel row held in w[]
 #define M1_ROW_BYTE_D(w, j) byte_to_double((w)[(j) >> 2], (j) & 3)
 
-// Fast tile: 16 pixels x 2 rows of macroblock `k` of the chunk, rows 2*qy, 2*qy+1 of the
-// macroblock row; everything in range and 16-byte aligned.  128-bit loads, conversion-free FP64,
-// 128-bit swizzled stores of int32 samples; the 2x2 chroma mean (source/image_processing.c:126-130)
-// stays inside the thread.
+// Fast half-tile: 8 pixels x 2 rows = the 2x8 strip of luma block column `bc` of the chunk in rows
+// 2*qy, 2*qy+1 of the macroblock row, plus the four 2x2 chroma means under it; everything in range
+// and aligned.  64/128-bit loads, one I2F.F64.U8 per byte (byte selector, no extraction ALU op),
+// 18 FP64 ops per pixel, 128-bit swizzled stores of int32 samples.  Called from a runtime loop so
+// the body exists once in the instruction stream.
 template <int CH>
-__device__ __forceinline__ void color_tile_fast(const uint8_t *__restrict__ row0, size_t pitch, int k, int qy,
-                                                int C, int *__restrict__ planes)
+struct HalfTilePixels { uint32_t w[2][2 * CH]; };   // the raw bytes of 8 pixels x 2 rows, in registers
+
+template <int CH>
+__device__ __forceinline__ HalfTilePixels<CH> load_half_tile(const uint8_t *__restrict__ row0, size_t pitch)
 {
-    uint32_t w0[4 * CH], w1[4 * CH];
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-        const uint4 a = __ldg((const uint4 *)row0 + i);
-        w0[4 * i] = a.x; w0[4 * i + 1] = a.y; w0[4 * i + 2] = a.z; w0[4 * i + 3] = a.w;
-    }
-#pragma unroll
-    for (int i = 0; i < CH; ++i) {
-        const uint4 a = __ldg((const uint4 *)(row0 + pitch) + i);
-        w1[4 * i] = a.x; w1[4 * i + 1] = a.y; w1[4 * i + 2] = a.z; w1[4 * i + 3] = a.w;
-    }
-    int sb[8], sr[8];
+    HalfTilePixels<CH> px;
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
-        const int rr = 2 * qy + dy, by = rr >> 3, r = rr & 7;
+        const uint8_t *p = row0 + dy * pitch;
+        if (CH == 4) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {                 // the two 8x8 luma blocks the tile touches
-            const int blk = by * 2 * C + 2 * k + h;
+            for (int i = 0; i < 2; ++i) {
+                const uint4 a = __ldg((const uint4 *)p + i);
+                px.w[dy][4 * i] = a.x; px.w[dy][4 * i + 1] = a.y; px.w[dy][4 * i + 2] = a.z; px.w[dy][4 * i + 3] = a.w;
+            }
+        } else {
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {             // 4-pixel groups = 16-byte chunks
-                int yv[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int i = 8 * h + 4 * j + e;  // pixel 0..15 of the tile row
-                    const double R = dy ? M1_ROW_BYTE_D(w1, CH * i) : M1_ROW_BYTE_D(w0, CH * i);
-                    const double G = dy ? M1_ROW_BYTE_D(w1, CH * i + 1) : M1_ROW_BYTE_D(w0, CH * i + 1);
-                    const double B = dy ? M1_ROW_BYTE_D(w1, CH * i + 2) : M1_ROW_BYTE_D(w0, CH * i + 2);
-                    int cb, cr;
-                    ycbcr_from_doubles(R, G, B, yv[e], cb, cr);
-                    if (dy == 0 && (e & 1) == 0) { sb[i >> 1] = cb; sr[i >> 1] = cr; }
-                    else                         { sb[i >> 1] += cb; sr[i >> 1] += cr; }
-                }
-                *(int4 *)(planes + chunk_word(blk, r * 2 + j)) = make_int4(yv[0], yv[1], yv[2], yv[3]);
+            for (int i = 0; i < 3; ++i) {
+                const uint2 a = __ldg((const uint2 *)p + i);
+                px.w[dy][2 * i] = a.x; px.w[dy][2 * i + 1] = a.y;
             }
         }
     }
-#pragma unroll
-    for (int j = 0; j < 2; ++j) {
-        *(int4 *)(planes + chunk_word(4 * C + k, qy * 2 + j)) =
-            make_int4(sb[4 * j] >> 2, sb[4 * j + 1] >> 2, sb[4 * j + 2] >> 2, sb[4 * j + 3] >> 2);
-        *(int4 *)(planes + chunk_word(5 * C + k, qy * 2 + j)) =
-            make_int4(sr[4 * j] >> 2, sr[4 * j + 1] >> 2, sr[4 * j + 2] >> 2, sr[4 * j + 3] >> 2);
-    }
+    return px;
 }
 
-// Generic tile: any alignment / channel count, coordinates clamped to the picture (= edge
-// replication up to the coded size).
-__device__ __noinline__ void color_tile_generic(const uint8_t *__restrict__ fr, const M1Geom &g, int x0, int y0,
-                                                int k, int qy, int C, int *__restrict__ planes)
+// (A non-inlined variant with both half-tiles' loads issued up front was measured 10 % slower:
+// the call pins the raw pixels in registers across the 460-instruction body.)
+template <int CH>
+__device__ __forceinline__ void convert_half_tile(const HalfTilePixels<CH> px, int bc, int qy, int C, int *__restrict__ planes)
 {
-    for (int qx = 0; qx < 8; ++qx) {
+    const uint32_t (&w)[2][2 * CH] = px.w;
+    int sb[4], sr[4];
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy) {
+        const int rr = 2 * qy + dy, by = rr >> 3, r = rr & 7;
+        const int blk = by * 2 * C + bc;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {                 // 4-pixel groups = 16-byte chunks
+            int yv[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = 4 * j + e;              // pixel 0..7 of the row
+                int cb, cr;
+                ycbcr_from_doubles(M1_ROW_BYTE_D(w[dy], CH * i), M1_ROW_BYTE_D(w[dy], CH * i + 1),
+                                   M1_ROW_BYTE_D(w[dy], CH * i + 2), yv[e], cb, cr);
+                if (dy == 0 && (e & 1) == 0) { sb[i >> 1] = cb; sr[i >> 1] = cr; }
+                else                         { sb[i >> 1] += cb; sr[i >> 1] += cr; }
+            }
+            *(int4 *)(planes + chunk_word(blk, r * 2 + j)) = make_int4(yv[0], yv[1], yv[2], yv[3]);
+        }
+    }
+    const int k = bc >> 1, h = bc & 1;                // macroblock, left/right half of its chroma row
+    *(int4 *)(planes + chunk_word(4 * C + k, qy * 2 + h)) = make_int4(sb[0] >> 2, sb[1] >> 2, sb[2] >> 2, sb[3] >> 2);
+    *(int4 *)(planes + chunk_word(5 * C + k, qy * 2 + h)) = make_int4(sr[0] >> 2, sr[1] >> 2, sr[2] >> 2, sr[3] >> 2);
+}
+
+template <int CH>
+__device__ __forceinline__ void color_half_tile(const uint8_t *__restrict__ row0, size_t pitch, int bc, int qy,
+                                                int C, int *__restrict__ planes)
+{
+    convert_half_tile<CH>(load_half_tile<CH>(row0, pitch), bc, qy, C, planes);
+}
+
+// Generic half-tile: any alignment / channel count, coordinates clamped to the picture (= edge
+// replication up to the coded size).
+__device__ __noinline__ void color_half_tile_generic(const uint8_t *__restrict__ fr, const M1Geom &g, int x0, int y0,
+                                                     int bc, int qy, int C, int *__restrict__ planes)
+{
+    for (int qx = 0; qx < 4; ++qx) {
         int sb = 0, sr = 0;
 #pragma unroll
         for (int dy = 0; dy < 2; ++dy)
@@ -353,19 +373,21 @@ __device__ __noinline__ void color_tile_generic(const uint8_t *__restrict__ fr, 
                 int yy, cb, cr;
                 ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
                 const int rr = 2 * qy + dy, cc = 2 * qx + dx;
-                planes[plane_word((rr >> 3) * 2 * C + 2 * k + (cc >> 3), rr & 7, cc & 7)] = yy;
+                planes[plane_word((rr >> 3) * 2 * C + bc, rr & 7, cc)] = yy;
                 sb += cb; sr += cr;
             }
-        planes[plane_word(4 * C + k, qy, qx)] = sb >> 2;
-        planes[plane_word(5 * C + k, qy, qx)] = sr >> 2;
+        planes[plane_word(4 * C + (bc >> 1), qy, 4 * (bc & 1) + qx)] = sb >> 2;
+        planes[plane_word(5 * C + (bc >> 1), qy, 4 * (bc & 1) + qx)] = sr >> 2;
     }
 }
 
 // -------------------------------------------------------------------------------------------
 // k_encode_chunks: one CTA per (chunk, slice, picture).
 // -------------------------------------------------------------------------------------------
-template <bool kLevels>
-__global__ void __launch_bounds__(256, 3)
+// kLoad: 3 / 4 = FULL mode with aligned 3- / 4-byte pixels (fast half-tiles), 0 = FULL mode generic
+// loads only, -1 = REF_COMPAT.  One instantiation per input format keeps each kernel's code small.
+template <int kLoad, bool kLevels>
+__global__ void __launch_bounds__(128, 6)
 k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quant q,
                 const uint8_t *__restrict__ rgb, const M1Tables *__restrict__ gtab,
                 uint32_t *__restrict__ staging, uint32_t *__restrict__ chunk_bits,
@@ -391,16 +413,20 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
     const uint8_t *fr = rgb + (size_t)frame * g.frame_stride;
 
     // ---- phase 1: colour conversion into the chunk's planes --------------------------------
-    if (g.mode == 0) {
-        // FULL: slice = macroblock row; tile = macroblock k of the chunk, row pair qy.
+    if (g.debug_skip & 1) {
+        // profiling only: leave the planes as they are
+    } else if (kLoad >= 0) {
+        // FULL: slice = macroblock row; half-tile = luma block column bc of the chunk, row pair qy.
         const size_t pitch = (size_t)g.W * g.channels;
-        for (int tile = tid; tile < 8 * nmb; tile += nthr) {
-            const int qy = tile / nmb, k = tile - qy * nmb;
-            const int x0 = 16 * (mb0 + k), y0 = 16 * slice + 2 * qy;
-            const bool inside = (x0 + 16 <= g.W) && (y0 + 2 <= g.H);
-            if (inside && g.fast_load == 3)      color_tile_fast<3>(fr + (size_t)y0 * pitch + (size_t)x0 * 3, pitch, k, qy, C, planes);
-            else if (inside && g.fast_load == 4) color_tile_fast<4>(fr + (size_t)y0 * pitch + (size_t)x0 * 4, pitch, k, qy, C, planes);
-            else                                 color_tile_generic(fr, g, x0, y0, k, qy, C, planes);
+        const int nbc = 2 * nmb;
+        constexpr int kCh = kLoad > 0 ? kLoad : 3;
+#pragma unroll 1
+        for (int ht = tid; ht < 8 * nbc; ht += nthr) {
+            const int qy = ht / nbc, bc = ht - qy * nbc;
+            const int x0 = 16 * mb0 + 8 * bc, y0 = 16 * slice + 2 * qy;
+            const bool inside = (x0 + 8 <= g.W) && (y0 + 2 <= g.H);
+            if (kLoad > 0 && inside) color_half_tile<kCh>(fr + (size_t)y0 * pitch + (size_t)x0 * kCh, pitch, bc, qy, C, planes);
+            else                     color_half_tile_generic(fr, g, x0, y0, bc, qy, C, planes);
         }
     } else {
         // REF_COMPAT (include/encoder.h:238-348): "slice" s is the 16-pixel column x = 16*s, the
@@ -426,6 +452,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
         }
     }
     __syncthreads();
+    if (g.debug_skip & 2) return;                           // profiling only
 
     // ---- phase 2: one thread per 8x8 block, threads in CODING order (t = 6*mb + blk), so the
     // bit offsets are a plain scan over the thread index.  pb = the thread's plane block.
@@ -547,6 +574,8 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
     if (tid == 0)
         chunk_bits[(size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk] = (uint32_t)total_bits;
 }
+
+#include "m1cu_encode_ws.cuh"
 
 // -------------------------------------------------------------------------------------------
 // k_layout: one CTA per picture.  Slice s starts at a byte boundary (include/encoder.h:442-443);
@@ -740,23 +769,56 @@ size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
 
 int m1k_encode_threads(const M1Geom &g) { return (8 * g.chunk_mbs + 31) & ~31; }   // one colour tile per thread; 6C of them own a block
 
+typedef void (*encode_kernel_t)(const M1Geom, const M1Quant, const uint8_t *, const M1Tables *, uint32_t *, uint32_t *,
+                                short *, int *);
+
+static encode_kernel_t pick_encode_kernel(const M1Geom &g, bool levels)
+{
+    if (g.mode != 0) return levels ? k_encode_chunks<-1, true> : k_encode_chunks<-1, false>;
+    if (g.fast_load == 3) return levels ? k_encode_chunks<3, true> : k_encode_chunks<3, false>;
+    if (g.fast_load == 4) return levels ? k_encode_chunks<4, true> : k_encode_chunks<4, false>;
+    return levels ? k_encode_chunks<0, true> : k_encode_chunks<0, false>;
+}
+
 cudaError_t m1k_prepare(const M1Geom &g)
 {
     const size_t smem = m1k_encode_smem_bytes(g, m1k_encode_threads(g));
-    cudaError_t e = cudaFuncSetAttribute(k_encode_chunks<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_encode_chunks<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    M1Geom v = g;
+    // every variant this geometry can be launched with (an unaligned input pointer falls back to 0)
+    for (int fl : { g.fast_load, 0 }) {
+        v.fast_load = fl;
+        for (bool lv : { false, true }) {
+            cudaError_t e = cudaFuncSetAttribute(pick_encode_kernel(v, lv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+    }
+    if (ws_kernel_for(g, false)) {
+        for (bool lv : { false, true }) {
+            cudaError_t e = cudaFuncSetAttribute(ws_kernel_for(g, lv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m1k_ws_smem_bytes());
+            if (e != cudaSuccess) return e;
+        }
+    }
+    return cudaSuccess;
 }
 
 cudaError_t m1k_launch_encode(const M1Geom &g, const M1Quant &q, const uint8_t *rgb, int n_frames,
                               const M1Tables *tables, uint32_t *staging, uint32_t *chunk_bits,
                               short *levels, int *err, cudaStream_t st)
 {
+    if (ws_kernel_t ws = ws_kernel_for(g, levels != nullptr)) {
+        // persistent warp-specialised kernel: one CTA per residency slot (3 per SM), chunks strided over them
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int n_chunks = g.chunks_per_frame * n_frames;
+        const int grid = n_chunks < 3 * sms ? n_chunks : 3 * sms;
+        ws<<<grid, M1_WS_THREADS, m1k_ws_smem_bytes(), st>>>(g, rgb, tables, n_chunks, staging, chunk_bits, levels, err);
+        return cudaGetLastError();
+    }
     const int threads = m1k_encode_threads(g);
     const size_t smem = m1k_encode_smem_bytes(g, threads);
     dim3 grid(g.chunks_per_slice, g.slices, n_frames);
-    if (levels) k_encode_chunks<true><<<grid, threads, smem, st>>>(g, q, rgb, tables, staging, chunk_bits, levels, err);
-    else        k_encode_chunks<false><<<grid, threads, smem, st>>>(g, q, rgb, tables, staging, chunk_bits, levels, err);
+    pick_encode_kernel(g, levels != nullptr)<<<grid, threads, smem, st>>>(g, q, rgb, tables, staging, chunk_bits, levels, err);
     return cudaGetLastError();
 }
 

@@ -10,7 +10,7 @@ print('fps', round(d['value']), 'ms/step', round(d['ms_per_step'], 3), 'frac', r
 PY
 if [ "$1" = "ncu" ]; then
   python bench.py --steps 1 --warmup 3 --frames 40 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 && \
-  ncu --set full --clock-control none --import-source on -k regex:k_encode_chunks -s 3 -c 1 -o gpurun_out/prof_$2 \
+  ncu --set full --clock-control none --import-source on -k regex:k_encode -s 3 -c 1 -o gpurun_out/prof_$2 \
       python bench.py --steps 1 --warmup 3 --frames 40 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
   tail -1 gpurun_out/ncu2.log
 fi

@@ -28,4 +28,4 @@ for k, v in tot.most_common(28): print(f"  {k:24s} {v:12d} {100*v/total:6.2f}%")
 for rg in sorted(reg):
     s = sum(reg[rg].values())
     print(f"== region {rg} (up to BAR #{rg+1}): {s} = {100*s/total:.1f}% of instructions, {regsamp[rg]} samples ==")
-    print("   " + ", ".join(f"{k}:{100*v/s:.0f}%" for k, v in reg[rg].most_common(12)))
+    print("   " + ", ".join(f"{k}:{100*v/max(s,1):.0f}%" for k, v in reg[rg].most_common(12)))
