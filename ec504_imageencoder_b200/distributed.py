@@ -51,7 +51,8 @@ def gather_to_rank0(out: torch.Tensor, frame_bytes: torch.Tensor, frame_offsets:
     meta[nmax:nmax + n + 1] = frame_offsets[:n + 1]
     metas = [torch.empty_like(meta) for _ in range(world)]
     dist.all_gather(metas, meta, group=group)
-    ends = [int(m[nmax + frames_per_rank[k]].item()) for k, m in enumerate(metas)]   # segment lengths, on the host
+    # segment lengths must be known on the host to post the receives: ONE small device->host copy
+    ends = torch.stack([m[nmax + frames_per_rank[k]] for k, m in enumerate(metas)]).cpu().tolist()
     # 2. payload segments: grouped send/recv into rank 0
     if rank == 0:
         need = sum(ends[1:])
