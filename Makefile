@@ -15,7 +15,7 @@ HOST    := $(PKG)/csrc/host
 OBJDIR  := $(HOST)/_build
 CFLAGS  := -O2 -g -fPIC -Iinclude -ffp-contract=off -Wall -Wno-unused-result
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared
-HOSTSRC := m1_bitvector.c m1_stream.c m1_vlc.c m1_blk.c m1_stages.c m1_driver.c m1_stb_stub.c
+HOSTSRC := m1_bitvector.c m1_stream.c m1_vlc.c m1_blk.c m1_stages.c m1_decode_helpers.c m1_driver.c m1_stb_stub.c
 HOSTOBJ := $(addprefix $(OBJDIR)/,$(HOSTSRC:.c=.o))
 # stb_image v2.30 (public domain): compiled from the copy the reference vendors, or from STB_IMAGE_H
 STB_IMAGE_H ?= /root/reference/include/stb_image.h

@@ -158,8 +158,10 @@ class M1Encoder:
             self._err(rc)
 
     # -- host-buffer path (what the C driver uses) ---------------------------------------------
-    def encode_host(self, rgb: np.ndarray | torch.Tensor, want_levels: bool = False, out: np.ndarray | None = None):
-        """rgb: uint8 host array/tensor [n, H, W, C].  Returns (payload list, levels or None)."""
+    def encode_host(self, rgb: np.ndarray | torch.Tensor, want_levels: bool = False, out: np.ndarray | None = None,
+                    copy: bool = True):
+        """rgb: uint8 host array/tensor [n, H, W, C].  Returns (payload list, levels or None).
+        copy=False returns numpy views into the output buffer instead of bytes objects."""
         if isinstance(rgb, torch.Tensor):
             assert not rgb.is_cuda
             src_ptr, n, keep = rgb.data_ptr(), rgb.shape[0], rgb
@@ -185,7 +187,10 @@ class M1Encoder:
                 self._err(rc)
             break
         offs = np.concatenate([[0], np.cumsum(sizes.astype(np.int64))])
-        payloads = [buf[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(n)]
+        if copy:
+            payloads = [buf[int(offs[i]):int(offs[i + 1])].tobytes() for i in range(n)]
+        else:
+            payloads = [buf[int(offs[i]):int(offs[i + 1])] for i in range(n)]
         return payloads, lev
 
     # -- utilities ---------------------------------------------------------------------------------
