@@ -20,7 +20,8 @@ encode_blk_coeff encode_block_end encode_block_header_i encode_coeff_sz_fast enc
 encode_macblk_encoding_value encode_macroblock_end encode_macroblock_header_i equalize_coefficients extract_8x8_block
 fast_DCT mpeg1_file_header mpeg1_gop mpeg1_packet_header mpeg1_picture_header mpeg1_sequence_end mpeg1_sequence_header
 mpeg1_slice mpeg1_sys_header print_array quantization run_length_encode scale_quantization_matrix subsampling_420
-write_to_bitstream zigzag_scanning mpeg_encode_procedure
+write_to_bitstream zigzag_scanning mpeg_encode_procedure DCT IDCT fast_IDCT dequantization upsampling insert_8x8_block
+convert_ycbcr_to_rgb concat_char
 Q_MATRIX ZIGZAG_ORDER START_FILE START_PICTURE blk_coeff_1_f blk_coeff_1_n blk_coeff_end blk_rle_lookup blk_rle_table
 dc_sz_chroma_table dc_sz_luma_table encoding_table mv_encoding_table slice_start_code""".split()
 
@@ -191,3 +192,49 @@ def test_mpeg_encode_procedure_return_codes(host, tmp_path):
     assert (tmp_path / "imgs").is_dir() and (tmp_path / "bs").is_dir() and v.stat().st_size == 27
     # empty images folder -> -1 (:175-183)
     assert host.mpeg_encode_procedure(str(tmp_path / "imgs"), str(tmp_path / "bs"), str(v)) == -1
+
+
+def test_decode_helpers_against_reference(host):
+    """the decoder-side exports, against the reference's own objects."""
+    import oracle
+    if not oracle.Ref.available():
+        pytest.skip("oracle/_ref not built")
+    L = host.lib()
+    R = C.CDLL(os.path.join(os.path.dirname(HERE), "oracle", "_ref", "libm1ref.so"))
+    rng = np.random.default_rng(8)
+    for i in range(40):
+        blk = rng.integers(0, 256, 64, dtype=np.uint8)
+        a, b = np.zeros(64, np.float32), np.zeros(64, np.float32)
+        L.DCT(blk.ctypes.data_as(C.c_void_p), a.ctypes.data_as(C.c_void_p))
+        R.DCT(blk.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(a, b)
+        pa, pb = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
+        L.IDCT(a.ctypes.data_as(C.c_void_p), pa.ctypes.data_as(C.c_void_p))
+        R.IDCT(a.ctypes.data_as(C.c_void_p), pb.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(pa, pb)
+        q = rng.integers(-40, 41, 64).astype(np.int32)
+        da, db = np.zeros(64, np.float64), np.zeros(64, np.float64)
+        L.dequantization(q.ctypes.data_as(C.c_void_p), da.ctypes.data_as(C.c_void_p))
+        R.dequantization(q.ctypes.data_as(C.c_void_p), db.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(da, db)
+        fa, fb = np.zeros(64, np.uint8), np.zeros(64, np.uint8)
+        L.fast_IDCT(da.ctypes.data_as(C.c_void_p), fa.ctypes.data_as(C.c_void_p))
+        R.fast_IDCT(da.ctypes.data_as(C.c_void_p), fb.ctypes.data_as(C.c_void_p))
+        assert np.array_equal(fa, fb)
+    W, H = 32, 16
+    cb, cr = rng.integers(0, 256, (H // 2) * (W // 2), dtype=np.uint8), rng.integers(0, 256, (H // 2) * (W // 2), dtype=np.uint8)
+    for lib_ in (L, R):
+        lib_.upsampling.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+        lib_.insert_8x8_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    outs = []
+    for lib_ in (L, R):
+        p, q2 = C.c_void_p(), C.c_void_p()
+        lib_.upsampling(cb.ctypes.data, cr.ctypes.data, W, H, C.byref(p), C.byref(q2))
+        outs.append((C.string_at(p, W * H), C.string_at(q2, W * H)))
+    assert outs[0] == outs[1]
+    assert np.array_equal(np.frombuffer(outs[0][0], np.uint8).reshape(H, W)[::2, ::2], cb.reshape(H // 2, W // 2))
+    plane_a, plane_b = np.zeros((24, 40), np.uint8), np.zeros((24, 40), np.uint8)
+    blk = rng.integers(0, 256, (8, 8), dtype=np.uint8)
+    L.insert_8x8_block(plane_a.ctypes.data, 40, 16, 8, blk.ctypes.data)
+    R.insert_8x8_block(plane_b.ctypes.data, 40, 16, 8, blk.ctypes.data)
+    assert np.array_equal(plane_a, plane_b) and np.array_equal(plane_a[8:16, 16:24], blk)
