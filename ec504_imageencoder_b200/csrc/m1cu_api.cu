@@ -49,6 +49,12 @@ struct m1cu_ctx {
     int16_t *d_levels = nullptr; size_t d_levels_cap = 0;
     uint8_t *h_out = nullptr;  size_t h_out_cap = 0;       // pinned bounce buffer
     uint32_t *h_fbytes = nullptr; unsigned long long *h_foff = nullptr; int h_meta_frames = 0;
+    // pipelined host path (encode_host_pipelined)
+    cudaStream_t copy_stream = nullptr, back_stream = nullptr;
+    std::vector<cudaEvent_t> pipe_events;
+    uint32_t *p_fbytes = nullptr, *ph_fbytes = nullptr;
+    unsigned long long *p_foff = nullptr, *ph_foff = nullptr;
+    int pipe_sub = 0, pipe_frames = 0;
     unsigned long long launches = 0;
     // optional per-kernel timing (m1cu_enable_timing)
     bool timing = false;
@@ -203,9 +209,10 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     CUC(cudaSetDevice(device));
     CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     ctx->own_stream = true;
-    // bound the staging memory: at most ~1 GiB of chunk records per launch round
+    // bound the staging memory: at most ~2 GiB of (worst-case sized, sparsely written) chunk records
+    // per launch round; 300 frames of 1080p fit in one round
     const size_t per_frame = (size_t)g.chunks_per_frame * g.chunk_stride;
-    size_t batch = ((size_t)1 << 30) / per_frame;
+    size_t batch = ((size_t)2 << 30) / per_frame;
     if (batch < 1) batch = 1;
     if (batch > (size_t)max_frames) batch = (size_t)max_frames;
     ctx->batch_frames = (int)batch;
@@ -240,6 +247,12 @@ int m1cu_destroy(m1cu_ctx *ctx)
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_fbytes) cudaFreeHost(ctx->h_fbytes);
     if (ctx->h_foff) cudaFreeHost(ctx->h_foff);
+    cudaFree(ctx->p_fbytes); cudaFree(ctx->p_foff);
+    if (ctx->ph_fbytes) cudaFreeHost(ctx->ph_fbytes);
+    if (ctx->ph_foff) cudaFreeHost(ctx->ph_foff);
+    for (auto e : ctx->pipe_events) cudaEventDestroy(e);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->back_stream) cudaStreamDestroy(ctx->back_stream);
     for (auto &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
     for (auto e : ctx->pool) cudaEventDestroy(e);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -338,6 +351,98 @@ int m1cu_check(m1cu_ctx *ctx)
     return M1CU_OK;
 }
 
+// Host-buffer path for long sequences: the input is uploaded in sub-batches on a copy stream while
+// earlier sub-batches are encoded on the compute stream and their payloads come back on a third
+// stream, so the call costs little more than the host->device copy of the RGB bytes (PCIe).
+// Every sub-batch owns a fixed region of d_out, so nothing has to be known on the host before the
+// next launch.  Returns M1CU_ERR_CAPACITY when a region overflows (the caller then takes the simple
+// path with worst-case sizing).
+static int encode_host_pipelined(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, uint8_t *h_out, size_t out_cap,
+                                 uint32_t *h_frame_bytes, size_t *total_bytes, int S)
+{
+    const M1Geom &g = ctx->g;
+    const int nsub = (n_frames + S - 1) / S;
+    const size_t region = m1cu_typical_out_bytes(ctx, S);
+    int rc;
+    if ((rc = ensure(ctx, (void **)&ctx->d_in, &ctx->d_in_cap, (size_t)g.frame_stride * n_frames))) return rc;
+    if ((rc = ensure(ctx, (void **)&ctx->d_out, &ctx->d_out_cap, region * nsub))) return rc;
+    if ((rc = ensure(ctx, (void **)&ctx->h_out, &ctx->h_out_cap, region * nsub, true))) return rc;
+    if (ctx->pipe_sub < nsub || ctx->pipe_frames < n_frames) {
+        cudaFree(ctx->p_fbytes); cudaFree(ctx->p_foff);
+        if (ctx->ph_fbytes) cudaFreeHost(ctx->ph_fbytes);
+        if (ctx->ph_foff) cudaFreeHost(ctx->ph_foff);
+        ctx->p_fbytes = nullptr; ctx->p_foff = nullptr; ctx->ph_fbytes = nullptr; ctx->ph_foff = nullptr;
+        CU(cudaMalloc(&ctx->p_fbytes, sizeof(uint32_t) * n_frames));
+        CU(cudaMalloc(&ctx->p_foff, sizeof(unsigned long long) * (size_t)nsub * (S + 1)));
+        CU(cudaMallocHost(&ctx->ph_fbytes, sizeof(uint32_t) * n_frames));
+        CU(cudaMallocHost(&ctx->ph_foff, sizeof(unsigned long long) * (size_t)nsub * (S + 1)));
+        ctx->pipe_sub = nsub; ctx->pipe_frames = n_frames;
+    }
+    if (!ctx->copy_stream) CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->back_stream) CU(cudaStreamCreateWithFlags(&ctx->back_stream, cudaStreamNonBlocking));
+    while ((int)ctx->pipe_events.size() < 3 * nsub) {
+        cudaEvent_t e; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        ctx->pipe_events.push_back(e);
+    }
+    cudaStream_t st = ctx->stream;
+    // the copy stream must not start before work already queued on the compute stream (e.g. a
+    // previous call's kernels still reading d_in)
+    cudaEvent_t start = ctx->pipe_events[0];
+    CU(cudaEventRecord(start, st));
+    CU(cudaStreamWaitEvent(ctx->copy_stream, start, 0));
+    // 1. enqueue everything that needs no host knowledge: uploads, encodes, metadata downloads
+    for (int s = 0; s < nsub; ++s) {
+        const int f0 = s * S, ns = n_frames - f0 < S ? n_frames - f0 : S;
+        cudaEvent_t up = ctx->pipe_events[3 * s + 1], enc = ctx->pipe_events[3 * s + 2];
+        CU(cudaMemcpyAsync(ctx->d_in + (size_t)f0 * g.frame_stride, h_rgb + (size_t)f0 * g.frame_stride,
+                           (size_t)ns * g.frame_stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+        CU(cudaEventRecord(up, ctx->copy_stream));
+        CU(cudaStreamWaitEvent(st, up, 0));
+        rc = m1cu_encode_device(ctx, ctx->d_in + (size_t)f0 * g.frame_stride, ns, ctx->d_out + (size_t)s * region, region,
+                                ctx->p_fbytes + f0, (uint64_t *)(ctx->p_foff + (size_t)s * (S + 1)), nullptr);
+        if (rc) return rc;
+        CU(cudaMemcpyAsync(ctx->ph_fbytes + f0, ctx->p_fbytes + f0, sizeof(uint32_t) * ns, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(ctx->ph_foff + (size_t)s * (S + 1), ctx->p_foff + (size_t)s * (S + 1),
+                           sizeof(unsigned long long) * (ns + 1), cudaMemcpyDeviceToHost, st));
+        CU(cudaEventRecord(enc, st));
+    }
+    // 2. as each sub-batch finishes: fetch exactly its payload bytes, then compact the previous one
+    size_t pos = 0;
+    int flags = 0;
+    auto compact = [&](int s) -> int {
+        const int f0 = s * S, ns = n_frames - f0 < S ? n_frames - f0 : S;
+        const unsigned long long *off = ctx->ph_foff + (size_t)s * (S + 1);
+        for (int i = 0; i < ns; ++i) {
+            const size_t nb = ctx->ph_fbytes[f0 + i];
+            if (pos + nb > out_cap) return M1CU_ERR_CAPACITY;
+            memcpy(h_out + pos, ctx->h_out + (size_t)s * region + off[i], nb);
+            h_frame_bytes[f0 + i] = (uint32_t)nb;
+            pos += nb;
+        }
+        return M1CU_OK;
+    };
+    for (int s = 0; s < nsub; ++s) {
+        const int f0 = s * S, ns = n_frames - f0 < S ? n_frames - f0 : S;
+        CU(cudaEventSynchronize(ctx->pipe_events[3 * s + 2]));
+        const size_t end = (size_t)ctx->ph_foff[(size_t)s * (S + 1) + ns];
+        if (end > region) flags |= M1_ERRBIT_CAPACITY;
+        else if (end) CU(cudaMemcpyAsync(ctx->h_out + (size_t)s * region, ctx->d_out + (size_t)s * region, end,
+                                         cudaMemcpyDeviceToHost, ctx->back_stream));
+        if (s > 0 && !flags) {
+            // payload s-1 was requested one iteration ago; wait for it, then copy it out while s streams
+            CU(cudaStreamSynchronize(ctx->back_stream));      // covers s-1 and (shortly) s
+            if ((rc = compact(s - 1))) return fail(ctx, rc, "m1cu_encode_host: h_out too small");
+        }
+    }
+    rc = m1cu_check(ctx);                                      // device-side flags of all sub-batches
+    if (rc) return rc;
+    if (flags) return fail(ctx, M1CU_ERR_CAPACITY, "payload region of a sub-batch overflowed");
+    CU(cudaStreamSynchronize(ctx->back_stream));
+    if ((rc = compact(nsub - 1))) return fail(ctx, rc, "m1cu_encode_host: h_out too small");
+    if (total_bytes) *total_bytes = pos;
+    return M1CU_OK;
+}
+
 int m1cu_encode_host(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, uint8_t *h_out, size_t out_cap,
                      uint32_t *h_frame_bytes, int16_t *h_levels, size_t *total_bytes)
 {
@@ -347,6 +452,17 @@ int m1cu_encode_host(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, uint8_t 
     const M1Geom &g = ctx->g;
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
+    {
+        // long sequences: overlap upload, encode and download (sub-batches of ~100 MB of input)
+        int S = (int)(((size_t)100 << 20) / (size_t)g.frame_stride);
+        if (S < 1) S = 1;
+        if (!h_levels && n_frames >= 3 * S) {
+            const int prc = encode_host_pipelined(ctx, h_rgb, n_frames, h_out, out_cap, h_frame_bytes, total_bytes, S);
+            if (prc != M1CU_ERR_CAPACITY) return prc;
+            CU(cudaDeviceSynchronize());                       // rare: fall through to worst-case sizing below
+            m1cu_check(ctx);
+        }
+    }
     const size_t in_bytes = (size_t)g.frame_stride * n_frames;
     int rc;
     if ((rc = ensure(ctx, (void **)&ctx->d_in, &ctx->d_in_cap, in_bytes))) return rc;

@@ -81,8 +81,12 @@ def test_config1_1080p_batch_properties(m1, port):
     assert hashlib.sha256(res2.out[:end].cpu().numpy().tobytes()).hexdigest() == \
            hashlib.sha256(res.out[:end].cpu().numpy().tobytes()).hexdigest()
     # host path == device path at full size
-    hp, _ = enc.encode_host(rgb[:40].cpu().numpy())
+    hp, _ = enc.encode_host(rgb[:40].cpu().numpy())           # short call: simple path
     assert hp == pays[:40]
+    hp, _ = enc.encode_host(rgb[:110].cpu().numpy())          # long call: pipelined upload / encode / download
+    assert hp == pays[:110]
+    hp, _ = enc.encode_host(rgb[:110].cpu().numpy())          # and again on the warmed-up context
+    assert hp == pays[:110]
 
 
 def test_config3_frame_ranges(m1, port):
