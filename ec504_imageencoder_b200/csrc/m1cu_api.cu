@@ -201,6 +201,11 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     // 128-bit tile loads need 16-pixel tiles to start on 16-byte boundaries in every row and picture
     g.fast_load = (mode == M1CU_MODE_FULL && (channels == 3 || channels == 4) && width % 16 == 0) ? channels : 0;
     g.debug_skip = getenv("M1_DEBUG_SKIP") ? atoi(getenv("M1_DEBUG_SKIP")) : 0;
+    g.win_words = M1_WIN_WORDS;
+    if (const char *v = getenv("M1_WIN_WORDS")) {          // test knob: force the multi-window path
+        const int w = atoi(v);
+        if (w >= 4 && w <= M1_WIN_WORDS) g.win_words = w;
+    }
 
     m1cu_qmatrix(quality, ctx->qm);
     if (!make_quant(ctx->qm, &ctx->q)) { delete ctx; return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: quantiser constants failed self-check"); }

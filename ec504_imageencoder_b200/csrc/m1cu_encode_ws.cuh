@@ -63,6 +63,7 @@ k_encode_ws(const __grid_constant__ M1Geom g, const uint8_t *__restrict__ rgb, c
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int C = g.chunk_mbs;                                   // <= M1_WS_CHUNK
+    const int WW = g.win_words;                                  // <= M1_WIN_WORDS (smaller only in tests)
 
     // shared memory carve-up
     int *planes0 = (int *)smem;                                                  // [STAGES][6*16 blocks][64]
@@ -197,15 +198,15 @@ k_encode_ws(const __grid_constant__ M1Geom g, const uint8_t *__restrict__ rgb, c
 
             mbar_wait(&wempty[w], wph ^ 1u);                     // the writer has emptied and re-zeroed this window
             uint32_t *out = staging + (size_t)cid * (g.chunk_stride / 4);
-            for (int w0 = 0;; w0 += 32 * M1_WIN_WORDS) {
+            for (int w0 = 0;; w0 += 32 * WW) {
                 if (bt == 0 && hdr_bits && w0 == 0) {
                     // source/mpeg1_blk.c:12-20: 000001 | (vertical_pos+1)&0xff | quant_scale(5)=1 | 0
-                    WindowWriter ww{win, 0, 0};
+                    WindowWriter ww{win, 0, 0, WW};
                     ww.put(1u, 24);
                     ww.put(((((uint32_t)(c.slice & 0xff) + 1u) & 0xffu) << 6) | (1u << 1), 14);
                 }
-                if (active && my_off < w0 + 32 * M1_WIN_WORDS && my_off + my_bits > w0) {
-                    if (my_bits <= 64 && my_off >= w0 && my_off + my_bits <= w0 + 32 * M1_WIN_WORDS) {
+                if (active && my_off < w0 + 32 * WW && my_off + my_bits > w0) {
+                    if (my_bits <= 64 && my_off >= w0 && my_off + my_bits <= w0 + 32 * WW) {
                         const int p = my_off - w0, word = p >> 5, o = p & 31;
                         const uint32_t a = acc.hi >> o;
                         const uint32_t b = __funnelshift_r(acc.lo, acc.hi, o);
@@ -214,17 +215,17 @@ k_encode_ws(const __grid_constant__ M1Geom g, const uint8_t *__restrict__ rgb, c
                         if (b) atomicOr(&win[word + 1], b);
                         if (cc) atomicOr(&win[word + 2], cc);
                     } else {
-                        WindowWriter ww{win, my_off, w0};        // long block, or one straddling the window
+                        WindowWriter ww{win, my_off, w0, WW};        // long block, or one straddling the window
                         if (blk == 0) ww.put(3u, 2);
                         code_block<64>(ww, rec, bt, nz, is_luma, tb);
                     }
                 }
-                if (w0 + 32 * M1_WIN_WORDS >= total_bits) break;
+                if (w0 + 32 * WW >= total_bits) break;
                 // rare: the chunk needs more than one window; the block warps flush and clear it themselves
                 block_bar();
-                for (int i = bt; i < M1_WIN_WORDS; i += M1_WS_BLOCK_THREADS) out[(w0 >> 5) + i] = win[i];
+                for (int i = bt; i < WW; i += M1_WS_BLOCK_THREADS) out[(w0 >> 5) + i] = win[i];
                 block_bar();
-                for (int i = bt; i < M1_WIN_WORDS + 2; i += M1_WS_BLOCK_THREADS) win[i] = 0;
+                for (int i = bt; i < WW + 2; i += M1_WS_BLOCK_THREADS) win[i] = 0;
                 block_bar();
             }
             if (bt == 0) wtotal[w] = total_bits;
@@ -241,7 +242,7 @@ k_encode_ws(const __grid_constant__ M1Geom g, const uint8_t *__restrict__ rgb, c
             uint32_t *out = staging + (size_t)cid * (g.chunk_stride / 4);
             mbar_wait(&wfull[w], wph);
             const int total_bits = wtotal[w];
-            const int w0 = ((total_bits - 1) / (32 * M1_WIN_WORDS)) * (32 * M1_WIN_WORDS);   // last window's first bit
+            const int w0 = ((total_bits - 1) / (32 * WW)) * (32 * WW);   // last window's first bit
             const int nwords = (total_bits - w0 + 31) >> 5;
             for (int i = lane; i < nwords; i += 32) { out[(w0 >> 5) + i] = win[i]; }
             for (int i = lane; i < nwords + 2 && i < M1_WIN_WORDS + 2; i += 32) win[i] = 0;

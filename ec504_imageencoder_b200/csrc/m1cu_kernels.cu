@@ -199,16 +199,17 @@ struct WindowWriter {
     uint32_t *win;
     int pos;   // absolute bit position in the chunk
     int w0;
+    int nw;    // window size in words (g.win_words)
     __device__ __forceinline__ void put(uint32_t code, int len)
     {
         const int p = pos - w0;
         pos += len;
-        if (p + len <= 0 || p >= 32 * M1_WIN_WORDS) return;
+        if (p + len <= 0 || p >= 32 * nw) return;
         const int word = p >> 5, o = p & 31;
         const unsigned long long sh = ((unsigned long long)code << (64 - len)) >> o;
         const uint32_t hi = (uint32_t)(sh >> 32), lo = (uint32_t)sh;
-        if (hi && word >= 0 && word < M1_WIN_WORDS) atomicOr(&win[word], hi);
-        if (lo && word + 1 >= 0 && word + 1 < M1_WIN_WORDS) atomicOr(&win[word + 1], lo);
+        if (hi && word >= 0 && word < nw) atomicOr(&win[word], hi);
+        if (lo && word + 1 >= 0 && word + 1 < nw) atomicOr(&win[word + 1], lo);
     }
 };
 
@@ -541,15 +542,16 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
 
     uint32_t *out = staging + ((size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk)
                                   * (g.chunk_stride / 4);
-    for (int w0 = 0;; w0 += 32 * M1_WIN_WORDS) {            // the window was zeroed at kernel start
+    const int WW = g.win_words;                             // <= M1_WIN_WORDS (smaller only in tests)
+    for (int w0 = 0;; w0 += 32 * WW) {            // the window was zeroed at kernel start
         if (tid == 0 && hdr_bits && w0 == 0) {
             // source/mpeg1_blk.c:12-20: 000001 | (vertical_pos+1)&0xff | quant_scale(5)=1 | 0
-            WindowWriter ww{win, 0, 0};
+            WindowWriter ww{win, 0, 0, WW};
             ww.put(1u, 24);
             ww.put(((((uint32_t)(slice & 0xff) + 1u) & 0xffu) << 6) | (1u << 1), 14);
         }
-        if (active && my_off < w0 + 32 * M1_WIN_WORDS && my_off + my_bits > w0) {
-            if (my_bits <= 64 && my_off >= w0 && my_off + my_bits <= w0 + 32 * M1_WIN_WORDS) {
+        if (active && my_off < w0 + 32 * WW && my_off + my_bits > w0) {
+            if (my_bits <= 64 && my_off >= w0 && my_off + my_bits <= w0 + 32 * WW) {
                 const int p = my_off - w0, word = p >> 5, o = p & 31;
                 const uint32_t a = acc.hi >> o;
                 const uint32_t b = __funnelshift_r(acc.lo, acc.hi, o);
@@ -558,17 +560,17 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
                 if (b) atomicOr(&win[word + 1], b);
                 if (c) atomicOr(&win[word + 2], c);
             } else {
-                WindowWriter ww{win, my_off, w0};           // long block, or one straddling the window
+                WindowWriter ww{win, my_off, w0, WW};           // long block, or one straddling the window
                 if (blk == 0) ww.put(3u, 2);
                 code_block(ww, rec, pb, nz, is_luma, tb);
             }
         }
         __syncthreads();
-        const int nwords = min(M1_WIN_WORDS, (total_bits - w0 + 31) >> 5);
+        const int nwords = min(WW, (total_bits - w0 + 31) >> 5);
         for (int i = tid; i < nwords; i += nthr) out[(w0 >> 5) + i] = win[i];
-        if (w0 + 32 * M1_WIN_WORDS >= total_bits) break;
+        if (w0 + 32 * WW >= total_bits) break;
         __syncthreads();                                    // rare: the chunk needs another window pass
-        for (int i = tid; i < M1_WIN_WORDS + 2; i += nthr) win[i] = 0;
+        for (int i = tid; i < WW + 2; i += nthr) win[i] = 0;
         __syncthreads();
     }
     if (tid == 0)

@@ -238,3 +238,55 @@ def test_decode_helpers_against_reference(host):
     L.insert_8x8_block(plane_a.ctypes.data, 40, 16, 8, blk.ctypes.data)
     R.insert_8x8_block(plane_b.ctypes.data, 40, 16, 8, blk.ctypes.data)
     assert np.array_equal(plane_a, plane_b) and np.array_equal(plane_a[8:16, 16:24], blk)
+
+
+@pytest.mark.gpu
+def test_mpeg_encode_procedure_on_a_jpeg_folder(host, port, tmp_path):
+    """The folder-scanning entry point end to end: JPEGs written here -> stb_image decode (host) ->
+    GPU encode -> host headers -> .mpeg + image_N.bit side files, against the oracle's stream built
+    from the same stb-decoded pixels in the same readdir order."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    PIL = pytest.importorskip("PIL.Image")
+    L = host.lib()
+
+    class Img(C.Structure):
+        _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("data", C.POINTER(C.c_ubyte))]
+    L.read_jpeg.restype = C.POINTER(Img)
+    L.read_jpeg.argtypes = [C.c_char_p]
+    L.free_image.argtypes = [C.POINTER(Img)]
+    imgs = tmp_path / "images"
+    imgs.mkdir()
+    rng = np.random.default_rng(3)
+    W, H = 208, 176
+    for i in range(4):
+        yy, xx = np.mgrid[0:H, 0:W]
+        a = np.stack([(xx * 255 // W + 20 * i) % 256, (yy * 255 // H) % 256, ((xx + yy) // 2 + rng.integers(0, 30, (H, W))) % 256], -1)
+        PIL.fromarray(a.astype(np.uint8)).save(str(imgs / f"pic_{i}.jpg"), quality=92)
+    probe = L.read_jpeg(str(imgs / "pic_0.jpg").encode())
+    if not probe:
+        pytest.skip("libencoder.so was built without stb_image.h")
+    L.free_image(probe)
+    video = tmp_path / "out" / "v.mpeg"
+    (tmp_path / "out").mkdir()
+    assert host.mpeg_encode_procedure(str(imgs), str(tmp_path / "out"), str(video), 12) == 0
+    frames = []
+    for name in os.listdir(imgs):                      # readdir order, like the driver
+        p = L.read_jpeg(str(imgs / name).encode())
+        assert p and p.contents.channels == 3
+        frames.append(np.ctypeslib.as_array(p.contents.data, shape=(H, W, 3)).copy())
+        L.free_image(p)
+    frames = np.stack(frames)
+    assert video.read_bytes() == port.encode_stream(frames, 12, 1)          # REF_COMPAT is the driver's default
+    # .bit side file: int32 width, height, then the full-resolution Y, Cb, Cr planes
+    bit = (tmp_path / "out" / "image_1.bit").read_bytes()
+    y, cb, cr = port.rgb_to_ycbcr(frames[0].reshape(-1, 3))
+    assert bit == np.array([W, H], np.int32).tobytes() + y.tobytes() + cb.tobytes() + cr.tobytes()
+    # M1_MODE=full: whole pictures
+    os.environ["M1_MODE"] = "full"
+    try:
+        assert host.mpeg_encode_procedure(str(imgs), str(tmp_path / "out"), str(video), 12) == 0
+    finally:
+        del os.environ["M1_MODE"]
+    assert video.read_bytes() == port.encode_stream(frames, 12, 0)
