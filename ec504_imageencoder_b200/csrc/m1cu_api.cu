@@ -317,9 +317,8 @@ int m1cu_encode_device(m1cu_ctx *ctx, const uint8_t *d_rgb, int n_frames, uint8_
     cudaStream_t st = ctx->stream;
     CU(cudaSetDevice(ctx->device));
     CU(cudaMemsetAsync(ctx->d_running, 0, sizeof(unsigned long long), st));
-    const int est_words = (int)(g.mbs_per_frame * 24 / 4);
-    int bx = est_words / 1024 + 1;
-    if (bx > 128) bx = 128;
+    int bx = (g.chunks_per_frame + 7) / 8;                     // k_stitch: one warp per chunk, 8 warps per CTA
+    if (bx > 512) bx = 512;
     for (int f0 = 0; f0 < n_frames; f0 += ctx->batch_frames) {
         const int nb = n_frames - f0 < ctx->batch_frames ? n_frames - f0 : ctx->batch_frames;
         {

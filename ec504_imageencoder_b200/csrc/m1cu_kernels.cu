@@ -687,33 +687,37 @@ k_stitch(const __grid_constant__ M1Geom g, const uint32_t *__restrict__ staging,
     const uint32_t *cd = chunk_dst + (size_t)f * g.chunks_per_frame;
     const int nc = g.chunks_per_frame;
     uint32_t *dst = (uint32_t *)(out + foff);
-    for (unsigned int w = blockIdx.x * blockDim.x + threadIdx.x; w < nwords; w += gridDim.x * blockDim.x) {
-        unsigned int b = w * 32u;
-        const unsigned int end = b + 32u;
-        // largest c with cd[c] <= b
-        int lo = 0, hi = nc - 1;
-        while (lo < hi) {
-            const int mid = (lo + hi + 1) >> 1;
-            if (cd[mid] <= b) lo = mid; else hi = mid - 1;
-        }
-        int c = lo;
-        uint32_t acc = 0;
-        while (b < end && c < nc) {
-            const unsigned int cs = cd[c], ce = cs + cb[c];
-            if (b < ce) {
-                const int take = (int)(min(end, ce) - b);
-                const uint32_t *src = staging + (size_t)((size_t)f * nc + c) * (g.chunk_stride / 4);
-                const uint32_t bits = read_bits(src, b - cs, take);
-                acc |= bits << (end - b - take);
-                b += take;
+    // One warp per chunk, no search: chunk c OWNS the output words whose first bit lies in
+    // [cd[c], cd[c+1]) (its own bits plus any slice padding behind it); a word that runs past the
+    // chunk's end pulls the rest from the following chunk(s).
+    const int lane = threadIdx.x & 31;
+    const int warps_per_row = (gridDim.x * blockDim.x) >> 5;
+    for (int c0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; c0 < nc; c0 += warps_per_row) {
+        const unsigned int own_lo = cd[c0];
+        const unsigned int own_hi = c0 + 1 < nc ? cd[c0 + 1] : nwords * 32u;
+        const unsigned int w_lo = (own_lo + 31u) >> 5, w_hi = min((own_hi + 31u) >> 5, nwords);
+        for (unsigned int w = w_lo + lane; w < w_hi; w += 32) {
+            unsigned int b = w * 32u;
+            const unsigned int end = b + 32u;
+            int c = c0;
+            uint32_t acc = 0;
+            while (b < end && c < nc) {
+                const unsigned int cs = cd[c], ce = cs + cb[c];
+                if (b < ce) {
+                    const int take = (int)(min(end, ce) - b);
+                    const uint32_t *src = staging + (size_t)((size_t)f * nc + c) * (g.chunk_stride / 4);
+                    const uint32_t bits = read_bits(src, b - cs, take);
+                    acc |= bits << (end - b - take);
+                    b += take;
+                }
+                if (b >= ce) {
+                    ++c;
+                    if (c < nc) { const unsigned int ns = cd[c]; if (ns > b) b = min(end, ns); }  // slice padding zeros
+                    else b = end;
+                }
             }
-            if (b >= ce) {
-                ++c;
-                if (c < nc) { const unsigned int ns = cd[c]; if (ns > b) b = min(end, ns); }  // slice padding zeros
-                else b = end;
-            }
+            dst[w] = __byte_perm(acc, 0, 0x0123);
         }
-        dst[w] = __byte_perm(acc, 0, 0x0123);
     }
 }
 
@@ -766,7 +770,8 @@ __global__ void k_synth_rgb(uint32_t seed, long first_frame, int n_frames, int W
 size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
 {
     (void)threads;
-    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 2) * 4 + sizeof(M1Tables) + 8 * sizeof(int) + 16;
+    static const size_t pad = getenv("M1_PAD_SMEM") ? (size_t)atoi(getenv("M1_PAD_SMEM")) : 0;   // occupancy experiments
+    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 2) * 4 + sizeof(M1Tables) + 8 * sizeof(int) + 16 + pad;
 }
 
 int m1k_encode_threads(const M1Geom &g) { return (8 * g.chunk_mbs + 31) & ~31; }   // one colour tile per thread; 6C of them own a block
