@@ -13,7 +13,7 @@ NVCC    ?= nvcc
 PKG     := ec504_imageencoder_b200
 HOST    := $(PKG)/csrc/host
 OBJDIR  := $(HOST)/_build
-CFLAGS  := -O2 -g -fPIC -Iinclude -ffp-contract=off -Wall -Wno-unused-result
+CFLAGS  := -O2 -g -fPIC -Iinclude -ffp-contract=off -Wall -Wno-unused-result -Wno-stringop-overflow
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared
 HOSTSRC := m1_bitvector.c m1_stream.c m1_vlc.c m1_blk.c m1_stages.c m1_decode_helpers.c m1_driver.c m1_stb_stub.c
 HOSTOBJ := $(addprefix $(OBJDIR)/,$(HOSTSRC:.c=.o))
