@@ -107,8 +107,10 @@ k_encode_ws(const __grid_constant__ M1Geom g, const uint8_t *__restrict__ rgb, c
             for (int ht = ct; ht < 8 * nbc; ht += M1_WS_COLOUR_THREADS) {
                 const int qy = ht / nbc, bc = ht - qy * nbc;
                 const int x0 = 16 * c.mb0 + 8 * bc, y0 = 16 * c.slice + 2 * qy;
-                if ((x0 + 8 <= g.W) && (y0 + 2 <= g.H))
-                    color_half_tile<CH>(fr + (size_t)y0 * pitch + (size_t)x0 * CH, pitch, bc, qy, C, planes);
+                const int ry = min(y0, g.H - 1);                 // rows below the picture replicate its last row
+                const size_t rp = (y0 + 1 <= g.H - 1) ? pitch : 0;
+                if (x0 + 8 <= g.W)
+                    color_half_tile<CH>(fr + (size_t)ry * pitch + (size_t)x0 * CH, rp, bc, qy, C, planes);
                 else
                     color_half_tile_generic(fr, g, x0, y0, bc, qy, C, planes);
             }

@@ -425,8 +425,12 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
         for (int ht = tid; ht < 8 * nbc; ht += nthr) {
             const int qy = ht / nbc, bc = ht - qy * nbc;
             const int x0 = 16 * mb0 + 8 * bc, y0 = 16 * slice + 2 * qy;
-            const bool inside = (x0 + 8 <= g.W) && (y0 + 2 <= g.H);
-            if (kLoad > 0 && inside) color_half_tile<kCh>(fr + (size_t)y0 * pitch + (size_t)x0 * kCh, pitch, bc, qy, C, planes);
+            // rows below the picture replicate its last row (edge replication up to the coded size):
+            // clamp the row and, when the second row would fall outside, read the same row twice
+            const bool inside = (x0 + 8 <= g.W);
+            const int ry = min(y0, g.H - 1);
+            const size_t rp = (y0 + 1 <= g.H - 1) ? pitch : 0;
+            if (kLoad > 0 && inside) color_half_tile<kCh>(fr + (size_t)ry * pitch + (size_t)x0 * kCh, rp, bc, qy, C, planes);
             else                     color_half_tile_generic(fr, g, x0, y0, bc, qy, C, planes);
         }
     } else {

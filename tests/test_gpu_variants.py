@@ -41,3 +41,21 @@ def test_kernel_variant(env):
     e = dict(os.environ, **env)
     out = subprocess.run([sys.executable, "-c", SNIPPET], env=e, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "VARIANT_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_sharded_example_matches_oracle(tmp_path):
+    """examples/encode_sharded.py: frame-range sharding + NCCL gather to rank 0 + host headers gives the
+    oracle's byte stream.  Runs with 2 ranks when the box has 2 GPUs, else with 1."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    n = 2 if torch.cuda.device_count() >= 2 else 1
+    out = str(tmp_path / "s.mpeg")
+    script = os.path.join(ROOT, "examples", "encode_sharded.py")
+    args = ["--frames", "7", "--width", "352", "--height", "240", "--out", out, "--verify"]
+    if n == 1:
+        cmd = [sys.executable, script] + args
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
+               "--master-addr", "127.0.0.1", "--master-port", "29591", script] + args
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SHARDED_VERIFY_OK" in r.stdout, r.stdout[-1500:] + r.stderr[-1500:]
