@@ -38,18 +38,22 @@ __device__ __forceinline__ double byte_to_double(uint32_t w, int b)   // b is a 
     asm("cvt.rn.f64.u8 %0, %1;" : "=d"(d) : "r"(s));
     return d;
 }
+// The seven non-trivial coefficients live in constant memory so the FP64 instructions take them as
+// constant-bank operands instead of re-materialising 64-bit immediates through uniform registers.
+__constant__ double kYcc[7] = { 0.299, 0.587, 0.114, 0.168736, 0.331264, 0.418688, 0.081312 };
+
 __device__ __forceinline__ void ycbcr_from_doubles(double rd, double gd, double bd, int &y, int &cb, int &cr)
 {
-    double t = __dadd_rn(__dmul_rn(0.299, rd), __dmul_rn(0.587, gd));
-    t = __dadd_rn(t, __dmul_rn(0.114, bd));
+    double t = __dadd_rn(__dmul_rn(kYcc[0], rd), __dmul_rn(kYcc[1], gd));
+    t = __dadd_rn(t, __dmul_rn(kYcc[2], bd));
     y = trunc_nonneg(t);
-    double u = __dsub_rn(128.0, __dmul_rn(0.168736, rd));
-    u = __dsub_rn(u, __dmul_rn(0.331264, gd));
+    double u = __dsub_rn(128.0, __dmul_rn(kYcc[3], rd));
+    u = __dsub_rn(u, __dmul_rn(kYcc[4], gd));
     u = __fma_rn(0.5, bd, u);
     cb = trunc_nonneg(u);
     double v = __fma_rn(0.5, rd, 128.0);
-    v = __dsub_rn(v, __dmul_rn(0.418688, gd));
-    v = __dsub_rn(v, __dmul_rn(0.081312, bd));
+    v = __dsub_rn(v, __dmul_rn(kYcc[5], gd));
+    v = __dsub_rn(v, __dmul_rn(kYcc[6], bd));
     cr = trunc_nonneg(v);
 }
 
