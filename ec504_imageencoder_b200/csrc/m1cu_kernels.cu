@@ -586,6 +586,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
 }
 
 #include "m1cu_encode_ws.cuh"
+#include "m1cu_encode_persist.cuh"
 
 // -------------------------------------------------------------------------------------------
 // k_layout: one CTA per picture.  Slice s starts at a byte boundary (include/encoder.h:442-443);
@@ -813,6 +814,13 @@ cudaError_t m1k_prepare(const M1Geom &g)
             if (e != cudaSuccess) return e;
         }
     }
+    if (persist_kernel_for(g, false)) {
+        for (bool lv : { false, true }) {
+            cudaError_t e = cudaFuncSetAttribute(persist_kernel_for(g, lv), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)m1k_persist_smem_bytes(g, m1k_encode_threads(g)));
+            if (e != cudaSuccess) return e;
+        }
+    }
     return cudaSuccess;
 }
 
@@ -831,6 +839,16 @@ cudaError_t m1k_launch_encode(const M1Geom &g, const M1Quant &q, const uint8_t *
         return cudaGetLastError();
     }
     const int threads = m1k_encode_threads(g);
+    if (persist_kernel_t pk = persist_kernel_for(g, levels != nullptr)) {
+        // persistent CTAs (5 per SM), chunks strided over them, next chunk's pixels prefetched by cp.async
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int n_chunks = g.chunks_per_frame * n_frames;
+        const int grid = n_chunks < 5 * sms ? n_chunks : 5 * sms;
+        pk<<<grid, threads, m1k_persist_smem_bytes(g, threads), st>>>(g, rgb, tables, n_chunks, staging, chunk_bits, levels, err);
+        return cudaGetLastError();
+    }
     const size_t smem = m1k_encode_smem_bytes(g, threads);
     dim3 grid(g.chunks_per_slice, g.slices, n_frames);
     pick_encode_kernel(g, levels != nullptr)<<<grid, threads, smem, st>>>(g, q, rgb, tables, staging, chunk_bits, levels, err);
