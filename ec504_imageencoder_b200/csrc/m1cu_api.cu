@@ -196,6 +196,11 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     g.chunks_per_slice = (g.mbs_per_slice + g.chunk_mbs - 1) / g.chunk_mbs;
     g.chunks_per_frame = g.chunks_per_slice * g.slices;
     g.mbs_per_frame = g.mbs_per_slice * g.slices;
+    {
+        const int last_mbs = g.mbs_per_slice - (g.chunks_per_slice - 1) * g.chunk_mbs;
+        g.inv_nbc[0] = (65536u + 2u * g.chunk_mbs - 1u) / (2u * g.chunk_mbs);
+        g.inv_nbc[1] = (65536u + 2u * last_mbs - 1u) / (2u * last_mbs);
+    }
     g.chunk_stride = (unsigned)align_up(((size_t)M1_SLICE_HDR_BITS + (size_t)g.chunk_mbs * M1_MB_MAX_BITS + 7) / 8 + 8, 16);
     g.frame_stride = (unsigned long long)width * height * channels;
     // 128-bit tile loads need 16-pixel tiles to start on 16-byte boundaries in every row and picture

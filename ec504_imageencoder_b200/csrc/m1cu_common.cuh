@@ -12,6 +12,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stddef.h>
 
 #define M1_MAX_CHUNK_MBS 16          // upper bound of macroblocks per chunk (CTA of 128 threads)
 #define M1_DEFAULT_CHUNK_MBS 16      // default target: 8*16 = 128 colour-tile threads, 6*16 = 96 block threads per CTA
@@ -34,6 +35,8 @@ struct M1Geom {
     int chunks_per_slice;
     int chunks_per_frame;
     int mbs_per_frame;
+    unsigned inv_nbc[2];       // ceil(2^16 / block columns) of a full chunk [0] and of a slice's last chunk [1]:
+                               // x / nbc == (x * inv) >> 16 for x < 2048 (splits a half-tile index without a division)
     unsigned chunk_stride;     // staging bytes per chunk (multiple of 16)
     unsigned long long frame_stride;   // input bytes per picture
 };
@@ -48,7 +51,14 @@ struct M1Quant {
     int tb[64];                // 2m - 2 : level != 0  <=>  (unsigned)(c + ta) > tb
 };
 
-struct M1Tables {
+// Non-zero test constants, one word per coefficient pair (see k_encode_chunks): lanes 0x7800 - m and
+// 0x8800 - m.  Passed by value as a kernel parameter so that the statically indexed uses read them
+// straight from the constant bank.
+struct M1NzKeys {
+    uint32_t ka[32], kb[32];
+};
+
+struct alignas(16) M1Tables {   // size is a multiple of 16 (copied to shared memory in 128-bit pieces)
     uint32_t ac[112];
     uint32_t dc[18];
     uint8_t  first[36];

@@ -332,10 +332,12 @@ __device__ __forceinline__ void convert_half_tile(const HalfTilePixels<CH> px, i
 {
     const uint32_t (&w)[2][2 * CH] = px.w;
     int sb[4], sr[4];
+    // The four 16-byte luma groups of this strip are chunks i0 .. i0+3 of one block (i0 = 4*(qy & 3)):
+    // chunk_word(blk, i0 + n) == a1 ^ (n << 2), one LOP3 per store instead of the full swizzle.
+    const int blk = (qy >> 2) * 2 * C + bc, i0 = (qy & 3) << 2;
+    const int a1 = chunk_word(blk, i0);
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
-        const int rr = 2 * qy + dy, by = rr >> 3, r = rr & 7;
-        const int blk = by * 2 * C + bc;
 #pragma unroll
         for (int j = 0; j < 2; ++j) {                 // 4-pixel groups = 16-byte chunks
             int yv[4];
@@ -348,7 +350,7 @@ __device__ __forceinline__ void convert_half_tile(const HalfTilePixels<CH> px, i
                 if (dy == 0 && (e & 1) == 0) { sb[i >> 1] = cb; sr[i >> 1] = cr; }
                 else                         { sb[i >> 1] += cb; sr[i >> 1] += cr; }
             }
-            *(int4 *)(planes + chunk_word(blk, r * 2 + j)) = make_int4(yv[0], yv[1], yv[2], yv[3]);
+            *(int4 *)(planes + (a1 ^ ((2 * dy + j) << 2))) = make_int4(yv[0], yv[1], yv[2], yv[3]);
         }
     }
     const int k = bc >> 1, h = bc & 1;                // macroblock, left/right half of its chroma row
@@ -391,9 +393,12 @@ __device__ __noinline__ void color_half_tile_generic(const uint8_t *__restrict__
 // -------------------------------------------------------------------------------------------
 // kLoad: 3 / 4 = FULL mode with aligned 3- / 4-byte pixels (fast half-tiles), 0 = FULL mode generic
 // loads only, -1 = REF_COMPAT.  One instantiation per input format keeps each kernel's code small.
+#ifndef M1_ENC_MIN_CTAS
+#define M1_ENC_MIN_CTAS 6
+#endif
 template <int kLoad, bool kLevels>
-__global__ void __launch_bounds__(128, 6)
-k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quant q,
+__global__ void __launch_bounds__(128, M1_ENC_MIN_CTAS)
+k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKeys nk,
                 const uint8_t *__restrict__ rgb, const M1Tables *__restrict__ gtab,
                 uint32_t *__restrict__ staging, uint32_t *__restrict__ chunk_bits,
                 short *__restrict__ levels, int *__restrict__ err)
@@ -408,12 +413,18 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
     // shared memory carve-up
     int *planes = (int *)smem;                                   // [6C blocks][64] int32, swizzled
     short *rec = (short *)smem;                                  // aliases planes (see layout note)
-    uint32_t *win = (uint32_t *)(planes + 6 * C * 64);           // [M1_WIN_WORDS + 2]
-    M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS + 2);
-    int *wtot = (int *)(tb + 1);                                 // [8] bits per warp
+    uint32_t *win = (uint32_t *)(planes + 6 * C * 64);           // [M1_WIN_WORDS + 4]
+    M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS + 4);         // 16-byte aligned
+    int *wtot = (int *)(tb + 1);                                 // [8] bits per warp, 16-byte aligned
 
-    for (int i = tid; i < (int)(sizeof(M1Tables) / 4); i += nthr) ((uint32_t *)tb)[i] = ((const uint32_t *)gtab)[i];
-    for (int i = tid; i < M1_WIN_WORDS + 2; i += nthr) win[i] = 0;
+    // Per-CTA prologue, kept short: the coder's tables up to qshift[] in 128-bit pieces (the non-zero
+    // keys come from the constant bank), and only the first blockDim.x window words zeroed -- a chunk
+    // that needs more (> 32 * blockDim.x bits) zeroes the rest once its size is known.
+    constexpr int kTabVecs = ((int)offsetof(M1Tables, ka) + 15) / 16;
+#pragma unroll 1
+    for (int i = tid; i < kTabVecs; i += nthr) ((uint4 *)tb)[i] = __ldg((const uint4 *)gtab + i);
+    win[tid] = 0;
+    if (tid < 8) wtot[tid] = 0;
 
     const uint8_t *fr = rgb + (size_t)frame * g.frame_stride;
 
@@ -421,21 +432,32 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
     if (g.debug_skip & 1) {
         // profiling only: leave the planes as they are
     } else if (kLoad >= 0) {
-        // FULL: slice = macroblock row; half-tile = luma block column bc of the chunk, row pair qy.
+        // FULL: slice = macroblock row.  A thread owns the 8-pixel x 4-row strip (block column bc of the
+        // chunk, row quad q4) = two half-tiles, so the index split and the pixel address are computed once
+        // and stepped by rows; 4 * nbc = 8 * nmb strips <= blockDim.x.
         const size_t pitch = (size_t)g.W * g.channels;
         const int nbc = 2 * nmb;
         constexpr int kCh = kLoad > 0 ? kLoad : 3;
+        const unsigned inv = (chunk == g.chunks_per_slice - 1) ? g.inv_nbc[1] : g.inv_nbc[0];
+        for (int st = tid; st < 4 * nbc; st += nthr) {
+            const int q4 = (int)(((unsigned)st * inv) >> 16), bc = st - q4 * nbc;
+            const int x0 = 16 * mb0 + 8 * bc;
+            int y = 16 * slice + 4 * q4;
+            if (kLoad > 0 && x0 + 8 <= g.W) {
+                // rows below the picture replicate its last row (edge replication up to the coded size):
+                // clamp the first row, then step by the pitch only while the next row exists
+                const int last = g.H - 1;
+                const uint8_t *row = fr + (size_t)min(y, last) * pitch + (size_t)x0 * kCh;
 #pragma unroll 1
-        for (int ht = tid; ht < 8 * nbc; ht += nthr) {
-            const int qy = ht / nbc, bc = ht - qy * nbc;
-            const int x0 = 16 * mb0 + 8 * bc, y0 = 16 * slice + 2 * qy;
-            // rows below the picture replicate its last row (edge replication up to the coded size):
-            // clamp the row and, when the second row would fall outside, read the same row twice
-            const bool inside = (x0 + 8 <= g.W);
-            const int ry = min(y0, g.H - 1);
-            const size_t rp = (y0 + 1 <= g.H - 1) ? pitch : 0;
-            if (kLoad > 0 && inside) color_half_tile<kCh>(fr + (size_t)ry * pitch + (size_t)x0 * kCh, rp, bc, qy, C, planes);
-            else                     color_half_tile_generic(fr, g, x0, y0, bc, qy, C, planes);
+                for (int h = 0; h < 2; ++h, y += 2) {
+                    const size_t rp = (y + 1 <= last) ? pitch : 0;
+                    color_half_tile<kCh>(row, rp, bc, 2 * q4 + h, C, planes);
+                    row += rp + ((y + 2 <= last) ? pitch : 0);
+                }
+            } else {
+                color_half_tile_generic(fr, g, x0, y, bc, 2 * q4, C, planes);
+                color_half_tile_generic(fr, g, x0, y + 2, bc, 2 * q4 + 1, C, planes);
+            }
         }
     } else {
         // REF_COMPAT (include/encoder.h:238-348): "slice" s is the 16-pixel column x = 16*s, the
@@ -501,7 +523,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
                 const int w = hblk * 16 + i, z = hblk * 32 + i;
                 const uint32_t p = (uint32_t)v[zz_raster(z)] | ((uint32_t)v[zz_raster(z + 16)] << 16);
                 pk[w] = p;
-                const uint32_t f = ((p + tb->ka[w]) | (tb->kb[w] - p)) & 0x80008000u;
+                const uint32_t f = ((p + nk.ka[w]) | (nk.kb[w] - p)) & 0x80008000u;
                 fl = f + (fl >> 1);
             }
             half[hblk] = fl;
@@ -541,17 +563,19 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1Quan
     }
 
     const int hdr_bits = chunk == 0 ? M1_SLICE_HDR_BITS : 0;
-    int base = hdr_bits, total_bits = hdr_bits;
-    {
-        const int nw = nthr >> 5;
-        for (int w = 0; w < nw; ++w) { const int t = wtot[w]; total_bits += t; if (w < warp) base += t; }
-    }
+    const int4 wt = *(const int4 *)wtot;                    // blockDim.x <= 128: at most four warps
+    const int total_bits = hdr_bits + wt.x + wt.y + wt.z + wt.w;
+    const int base = hdr_bits + (warp > 0 ? wt.x : 0) + (warp > 1 ? wt.y : 0) + (warp > 2 ? wt.z : 0);
     const int my_off = base + incl - my_bits;
 
     uint32_t *out = staging + ((size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk)
                                   * (g.chunk_stride / 4);
     const int WW = g.win_words;                             // <= M1_WIN_WORDS (smaller only in tests)
-    for (int w0 = 0;; w0 += 32 * WW) {            // the window was zeroed at kernel start
+    if (min(WW, (total_bits + 31) >> 5) + 2 > nthr) {       // uniform; rare at typical qualities
+        for (int i = nthr + tid; i < WW + 2; i += nthr) win[i] = 0;
+        __syncthreads();
+    }
+    for (int w0 = 0;; w0 += 32 * WW) {            // the window words in use are zero here
         if (tid == 0 && hdr_bits && w0 == 0) {
             // source/mpeg1_blk.c:12-20: 000001 | (vertical_pos+1)&0xff | quant_scale(5)=1 | 0
             WindowWriter ww{win, 0, 0, WW};
@@ -776,16 +800,18 @@ __global__ void k_synth_rgb(uint32_t seed, long first_frame, int n_frames, int W
 // -------------------------------------------------------------------------------------------
 // Launchers (called from m1cu_api.cu).
 // -------------------------------------------------------------------------------------------
+void m1k_nz_keys(const M1Quant &q, M1NzKeys *k);
+
 size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
 {
     (void)threads;
     static const size_t pad = getenv("M1_PAD_SMEM") ? (size_t)atoi(getenv("M1_PAD_SMEM")) : 0;   // occupancy experiments
-    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 2) * 4 + sizeof(M1Tables) + 8 * sizeof(int) + 16 + pad;
+    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 4) * 4 + sizeof(M1Tables) + 8 * sizeof(int) + 16 + pad;
 }
 
 int m1k_encode_threads(const M1Geom &g) { return (8 * g.chunk_mbs + 31) & ~31; }   // one colour tile per thread; 6C of them own a block
 
-typedef void (*encode_kernel_t)(const M1Geom, const M1Quant, const uint8_t *, const M1Tables *, uint32_t *, uint32_t *,
+typedef void (*encode_kernel_t)(const M1Geom, const M1NzKeys, const uint8_t *, const M1Tables *, uint32_t *, uint32_t *,
                                 short *, int *);
 
 static encode_kernel_t pick_encode_kernel(const M1Geom &g, bool levels)
@@ -851,7 +877,9 @@ cudaError_t m1k_launch_encode(const M1Geom &g, const M1Quant &q, const uint8_t *
     }
     const size_t smem = m1k_encode_smem_bytes(g, threads);
     dim3 grid(g.chunks_per_slice, g.slices, n_frames);
-    pick_encode_kernel(g, levels != nullptr)<<<grid, threads, smem, st>>>(g, q, rgb, tables, staging, chunk_bits, levels, err);
+    M1NzKeys nk;
+    m1k_nz_keys(q, &nk);
+    pick_encode_kernel(g, levels != nullptr)<<<grid, threads, smem, st>>>(g, nk, rgb, tables, staging, chunk_bits, levels, err);
     return cudaGetLastError();
 }
 
@@ -890,16 +918,23 @@ cudaError_t m1k_launch_synth(uint32_t seed, long first_frame, int n_frames, int 
     return cudaGetLastError();
 }
 
+void m1k_nz_keys(const M1Quant &q, M1NzKeys *k)
+{
+    for (int w = 0; w < 32; ++w) {
+        const int zlo = (w & 15) + ((w >> 4) << 5), zhi = zlo + 16;
+        const uint32_t mlo = (uint32_t)q.ta[zz_raster(zlo)] + 1u, mhi = (uint32_t)q.ta[zz_raster(zhi)] + 1u;
+        k->ka[w] = ((0x7800u - mhi) << 16) | (0x7800u - mlo);
+        k->kb[w] = ((0x8800u - mhi) << 16) | (0x8800u - mlo);
+    }
+}
+
 void m1k_fill_tables(M1Tables *t, const M1Quant &q)
 {
     for (int i = 0; i < 112; ++i) t->ac[i] = i < M1_AC_ENTRIES ? kM1AcTable[i] : 0u;
     for (int i = 0; i < 18; ++i) t->dc[i] = kM1DcSize[i];
     for (int i = 0; i < 36; ++i) t->first[i] = i < 33 ? kM1AcFirst[i] : 0;
     for (int z = 0; z < 64; ++z) { t->qmul[z] = q.mul[zz_raster(z)]; t->qshift[z] = q.shift[zz_raster(z)]; }
-    for (int w = 0; w < 32; ++w) {
-        const int zlo = (w & 15) + ((w >> 4) << 5), zhi = zlo + 16;
-        const uint32_t mlo = (uint32_t)q.ta[zz_raster(zlo)] + 1u, mhi = (uint32_t)q.ta[zz_raster(zhi)] + 1u;
-        t->ka[w] = ((0x7800u - mhi) << 16) | (0x7800u - mlo);
-        t->kb[w] = ((0x8800u - mhi) << 16) | (0x8800u - mlo);
-    }
+    M1NzKeys nk;
+    m1k_nz_keys(q, &nk);
+    for (int w = 0; w < 32; ++w) { t->ka[w] = nk.ka[w]; t->kb[w] = nk.kb[w]; }
 }

@@ -107,6 +107,46 @@ def test_color_all_2_24(m1, port):
     assert np.array_equal(Cr.cpu().numpy().ravel(), ocr)
 
 
+@pytest.mark.parametrize("channels", [3, 4])
+def test_colour_exception_heavy_pictures(m1, port, channels):
+    """Pictures made of the colours where the reference's double chain truncates below the exact
+    rational value (greys, r == g, g == b, 1000 | 299r+587g+114b): every pixel takes the integer
+    path's fix-up branch.  Quality 89 (the finest quantiser noise stays encodable at) keeps
+    single-sample differences visible in the levels."""
+    rng = np.random.default_rng(5)
+    W, H, n = 352, 240, 6
+    v = rng.integers(0, 256, (n, H, W, 3), dtype=np.uint8)
+    img = v.copy()
+    img[0] = v[0][..., :1]                                     # greys
+    img[1][..., 1] = img[1][..., 0]                            # r == g
+    img[2][..., 2] = img[2][..., 1]                            # g == b
+    img[3] = 0                                                 # black
+    img[3][:, W // 2:] = 255                                   # and white
+    base = 299 * v[4][..., 0].astype(np.int64) + 587 * v[4][..., 1].astype(np.int64)
+    hit = (base[..., None] + 114 * np.arange(256)) % 1000 == 0      # at most one b per (r, g)
+    ok = hit.any(axis=-1)
+    img[4][..., 2] = np.where(ok, hit.argmax(axis=-1), v[4][..., 2]).astype(np.uint8)
+    assert ok.mean() > 0.1
+    # img[5] stays random
+    if channels == 4:
+        img = np.concatenate([img, rng.integers(0, 256, (n, H, W, 1), dtype=np.uint8)], axis=3)
+    enc = m1.M1Encoder(W, H, channels, MODE_FULL, 89, max_frames=n)
+    hp, lev = enc.encode_host(img, want_levels=True)
+    for f in range(n):
+        rp, rl = port.encode_picture(np.ascontiguousarray(img[f][..., :3]), 89, MODE_FULL, want_levels=True)
+        assert np.array_equal(lev[f], rl), f"levels differ on frame {f}"
+        assert hp[f] == rp, f"payload differs on frame {f}"
+    # and the conversion itself, sample for sample
+    enc1 = m1.M1Encoder(W, H, 3, MODE_FULL, 1, max_frames=1)
+    for f in range(n):
+        rgb = torch.from_numpy(np.ascontiguousarray(img[f][..., :3])).cuda()
+        Y, Cb, Cr = enc1.ycbcr_planes(rgb)
+        oy, ocb, ocr = port.rgb_to_ycbcr(np.ascontiguousarray(img[f][..., :3]).reshape(-1, 3))
+        assert np.array_equal(Y.cpu().numpy().ravel(), oy)
+        assert np.array_equal(Cb.cpu().numpy().ravel(), ocb)
+        assert np.array_equal(Cr.cpu().numpy().ravel(), ocr)
+
+
 def test_unencodable_level_reported(m1, port):
     """quality 91 + a half-block vertical step gives a coded AC level of 308: the reference
     returns NULL from encode_blk_coeff and crashes (source/vlc.c:383); the oracle refuses the
