@@ -1,5 +1,6 @@
 #!/bin/sh
-# Round-end evidence: tests, bench (both arms), ncu launch list and one full capture of the top kernel.
+# Round-end evidence, part 1: tests, bench (both arms), ncu launch list of the bench command.
+# (tools/gpu_ncu_only.sh <tag> takes the full capture of the top kernel in a separate call.)
 set -x
 timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/final_reference_arm.json 2> gpurun_out/final_reference_arm.err
@@ -8,7 +9,4 @@ tail -1 gpurun_out/final_bench.json | python -c "import sys,json; d=json.loads(s
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/final_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu.log 2>&1
-python bench.py --steps 1 --warmup 3 --frames 40 --no-cpu-baseline > gpurun_out/plain2.log 2>&1 && \
-ncu --set full --clock-control none --import-source on -k regex:k_encode -s 3 -c 1 -o gpurun_out/prof_final \
-    python bench.py --steps 1 --warmup 3 --frames 40 --no-cpu-baseline > gpurun_out/ncu2.log 2>&1
-tail -1 gpurun_out/ncu2.log
+tail -2 gpurun_out/ncu.log | cut -c1-300
