@@ -182,7 +182,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
     from ec504_imageencoder_b200 import M1Encoder, MODE_FULL, SYNTH_NATURAL
-    from ec504_imageencoder_b200.distributed import gather_to_rank0
+    from ec504_imageencoder_b200.distributed import PeerGather
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -204,12 +204,14 @@ def run_ours(args):
     with torch.cuda.stream(stream):
         first = rank * n                                            # contiguous frame range per rank
         rgb = enc.synth_rgb(SEED, first, n, SYNTH_NATURAL)          # resident in HBM before timing
-        # N > 1: two output buffers, so the gather of step i (comm stream) overlaps the encode of step
-        # i + 1 (compute stream); the timed region ends after the last gather has landed on rank 0.
-        bufs = [enc.alloc_outputs(n) for _ in range(2 if world > 1 else 1)]
+        # N > 1 (PeerGather, staged): after a step's encode, a small copy kernel on a high-priority side
+        # stream pushes the rank's payload bytes into its region of rank 0's memory (NVLink peer stores),
+        # followed by one small all_gather of the frame sizes/offsets = completion fence; both overlap the
+        # next step's encode.  Two slots; the timed region ends after the last fence has completed on
+        # every rank.  (M1_PEER_DIRECT=1: k_stitch writes remotely instead, no push, not overlappable.)
+        pg = PeerGather(enc, n, slots=2, staged=os.environ.get("M1_PEER_DIRECT", "0") != "1") if world > 1 else None
+        bufs = [pg.batch(0), pg.batch(1)] if world > 1 else [enc.alloc_outputs(n)]
         res = bufs[0]
-        recv_buf = (torch.empty(enc.typical_out_bytes(n) * (world - 1), dtype=torch.uint8, device=dev)
-                    if world > 1 and rank == 0 else None)
         comm = torch.cuda.Stream(device=dev, priority=-1) if world > 1 else None
         done = [torch.cuda.Event() for _ in bufs]
         sent = [torch.cuda.Event() for _ in bufs]
@@ -219,7 +221,7 @@ def run_ours(args):
         def launch_gather(j):
             comm.wait_event(done[j])
             with torch.cuda.stream(comm):
-                gather_to_rank0(bufs[j].out, bufs[j].frame_bytes, bufs[j].frame_offsets, [n] * world, recv=recv_buf)
+                pg.finish(j)
                 sent[j].record(comm)
 
         def step():
@@ -331,8 +333,10 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "width": W, "height": H, "quality": QUALITY, "frames_per_gpu_per_step": n,
                        "l2": "per-step input (%.2f GB per GPU) exceeds L2; no flush needed" % (n * 3 * W * H / 1e9),
                        "timer": "CUDA events on the launching stream, max over ranks",
-                       "multi_gpu": ("contiguous frame ranges per rank; per-frame sizes + payload segments gathered to rank 0 over NCCL "
-                                     "inside the timed region, the gather of step i overlapping the encode of step i+1") if world > 1 else "single GPU"},
+                       "multi_gpu": ("contiguous frame ranges per rank; inside the timed region every rank pushes its payload bytes into "
+                                     "its region of rank 0's memory over NVLink (CUDA IPC peer mapping, copy kernel on a side stream), then one "
+                                     "all_gather of the per-frame sizes/offsets = completion fence; both overlap the next step's encode")
+                       if world > 1 else "single GPU"},
             "megapixels_per_s": fps * W * H / 1e6,
             "payload_bytes_per_frame": payload_bytes / n,
             "clocks": clocks,
@@ -352,6 +356,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
     if world > 1:
+        pg.close()
         dist.barrier()
         dist.destroy_process_group()
     if line is not None:

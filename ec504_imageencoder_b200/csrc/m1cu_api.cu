@@ -573,4 +573,47 @@ void  m1cu_pinned_free(void *p) { if (p) cudaFreeHost(p); }
 int   m1cu_memcpy_h2d(void *dst, const void *src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? M1CU_OK : M1CU_ERR_CUDA; }
 int   m1cu_memcpy_d2h(void *dst, const void *src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? M1CU_OK : M1CU_ERR_CUDA; }
 
+int m1cu_ipc_export(void *d_ptr, unsigned char handle[M1CU_IPC_HANDLE_BYTES])
+{
+    static_assert(sizeof(cudaIpcMemHandle_t) == M1CU_IPC_HANDLE_BYTES, "IPC handle size");
+    if (!d_ptr || !handle) return fail(nullptr, M1CU_ERR_ARG, "m1cu_ipc_export: bad argument");
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, d_ptr);
+    if (e != cudaSuccess) return fail(nullptr, M1CU_ERR_CUDA, "cudaIpcGetMemHandle", e);
+    memcpy(handle, &h, sizeof h);
+    return M1CU_OK;
+}
+
+int m1cu_ipc_open(int device, const unsigned char handle[M1CU_IPC_HANDLE_BYTES], void **d_ptr)
+{
+    if (!handle || !d_ptr) return fail(nullptr, M1CU_ERR_ARG, "m1cu_ipc_open: bad argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof h);
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail(nullptr, M1CU_ERR_CUDA, "cudaIpcOpenMemHandle", e);
+    return M1CU_OK;
+}
+
+int m1cu_ipc_close(int device, void *d_ptr)
+{
+    if (!d_ptr) return M1CU_OK;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaIpcCloseMemHandle(d_ptr);
+    if (e != cudaSuccess) return fail(nullptr, M1CU_ERR_CUDA, "cudaIpcCloseMemHandle", e);
+    return M1CU_OK;
+}
+
+int m1cu_push_payloads(m1cu_ctx *ctx, void *stream, uint8_t *dst, size_t dst_cap, const uint8_t *d_src,
+                       const uint64_t *d_frame_offsets, int n_frames)
+{
+    if (!ctx || !dst || !d_src || !d_frame_offsets || n_frames <= 0 || (((uintptr_t)dst | (uintptr_t)d_src) & 15))
+        return fail(ctx, M1CU_ERR_ARG, "m1cu_push_payloads: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    CU(m1k_launch_push(dst, d_src, (const unsigned long long *)d_frame_offsets + n_frames, (unsigned long long)dst_cap,
+                       stream ? (cudaStream_t)stream : ctx->stream));
+    ctx->launches += 1;
+    return M1CU_OK;
+}
+
 }  // extern "C"

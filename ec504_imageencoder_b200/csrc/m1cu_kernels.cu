@@ -772,6 +772,19 @@ __global__ void k_ycbcr_planes(const uint8_t *__restrict__ rgb, int channels, si
     }
 }
 
+// Copies the payload bytes [0, *end) of one encode call (end = frame_offsets[n], a multiple of 16) to
+// `dst`, which may be another GPU's memory mapped over NVLink (distributed.PeerGather, staged mode).
+// A few CTAs on a high-priority side stream: they slip in as the next step's encode CTAs retire.
+__global__ void __launch_bounds__(256)
+k_push_bytes(uint4 *__restrict__ dst, const uint4 *__restrict__ src, const unsigned long long *__restrict__ end,
+             unsigned long long cap)
+{
+    const unsigned long long n16 = min(*end, cap) >> 4;
+    for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n16;
+         i += (unsigned long long)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
 __device__ __forceinline__ uint32_t mix32(uint32_t x)
 {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -911,6 +924,13 @@ cudaError_t m1k_launch_planes(const uint8_t *rgb, int channels, size_t npix, uin
 {
     const int blocks = (int)((npix + 255) / 256 < 148 * 8 ? (npix + 255) / 256 : 148 * 8);
     k_ycbcr_planes<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(rgb, channels, npix, Y, Cb, Cr);
+    return cudaGetLastError();
+}
+
+cudaError_t m1k_launch_push(uint8_t *dst, const uint8_t *src, const unsigned long long *end, unsigned long long cap,
+                            cudaStream_t st)
+{
+    k_push_bytes<<<64, 256, 0, st>>>((uint4 *)dst, (const uint4 *)src, end, cap);
     return cudaGetLastError();
 }
 

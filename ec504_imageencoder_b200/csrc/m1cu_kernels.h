@@ -22,3 +22,5 @@ cudaError_t m1k_launch_planes(const uint8_t *rgb, int channels, size_t npix, uin
                               cudaStream_t st);
 cudaError_t m1k_launch_synth(uint32_t seed, long first_frame, int n_frames, int W, int H, int kind,
                              uint8_t *rgb, cudaStream_t st);
+cudaError_t m1k_launch_push(uint8_t *dst, const uint8_t *src, const unsigned long long *end, unsigned long long cap,
+                            cudaStream_t st);

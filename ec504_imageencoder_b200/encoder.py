@@ -47,9 +47,13 @@ class EncodedBatch:
     frame_bytes: torch.Tensor    # int32 [n] (bit pattern of uint32)
     frame_offsets: torch.Tensor  # int64 [n+1]
     levels: torch.Tensor | None  # int16 [n, macroblocks, 6, 64] or None
+    out_ptr: int | None = None   # raw device address used instead of `out` (peer memory of another
+    out_cap: int | None = None   # rank, see distributed.PeerGather) and its capacity in bytes
 
     def payloads(self) -> list[bytes]:
         """Copies the payloads to the host (synchronises)."""
+        if self.out_ptr is not None:
+            raise RuntimeError("this batch writes into another rank's memory; read it there (Gathered.payloads)")
         sizes = self.frame_bytes.cpu().numpy().astype(np.int64)
         offs = self.frame_offsets.cpu().numpy()
         end = int(offs[-1])
@@ -143,7 +147,9 @@ class M1Encoder:
         if res is None:
             res = self.alloc_outputs(n, want_levels)
         self._bind_stream()
-        rc = self.lib.m1cu_encode_device(self._h, rgb.data_ptr(), n, res.out.data_ptr(), res.out.numel(),
+        out_ptr = res.out.data_ptr() if res.out_ptr is None else res.out_ptr
+        out_cap = res.out.numel() if res.out_ptr is None else res.out_cap
+        rc = self.lib.m1cu_encode_device(self._h, rgb.data_ptr(), n, out_ptr, out_cap,
                                          res.frame_bytes.data_ptr(), res.frame_offsets.data_ptr(),
                                          res.levels.data_ptr() if res.levels is not None else None)
         if rc:
@@ -151,6 +157,16 @@ class M1Encoder:
         if check:
             self.check()
         return res
+
+    def push_payloads(self, res: EncodedBatch, dst_ptr: int, dst_cap: int, n_frames: int | None = None):
+        """Copies the payload bytes of a finished encode to `dst_ptr` (e.g. a peer mapping) with a small
+        kernel on torch's CURRENT stream; the caller orders that stream after the encode."""
+        s = torch.cuda.current_stream(self.device).cuda_stream or 1
+        rc = self.lib.m1cu_push_payloads(self._h, C.c_void_p(s), dst_ptr, int(dst_cap), res.out.data_ptr(),
+                                         res.frame_offsets.data_ptr(),
+                                         int(res.frame_bytes.numel() if n_frames is None else n_frames))
+        if rc:
+            self._err(rc)
 
     def check(self):
         rc = self.lib.m1cu_check(self._h)

@@ -5,7 +5,8 @@
         examples/encode_sharded.py --frames 64 --width 1920 --height 1080 --out /tmp/seq.mpeg [--verify]
 
 Every rank encodes its contiguous frame range on its own GPU; per-frame byte counts and the
-compressed segments are gathered to rank 0 over NCCL; rank 0 adds the host-side headers (with the
+compressed segments are gathered to rank 0 over NCCL (or, with --peer, written by every rank's
+stitch kernel straight into rank 0's memory over NVLink: distributed.PeerGather); rank 0 adds the host-side headers (with the
 GLOBAL frame index, which drives the time stamps) and writes the .mpeg.  --verify compares the file
 with the oracle's stream for the same synthetic frames (test infrastructure, CPU, slow).
 """
@@ -21,7 +22,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from ec504_imageencoder_b200 import M1Encoder, MODE_FULL, SYNTH_NATURAL, hostlib  # noqa: E402
-from ec504_imageencoder_b200.distributed import frame_range, gather_to_rank0  # noqa: E402
+from ec504_imageencoder_b200.distributed import PeerGather, frame_range, gather_to_rank0  # noqa: E402
 
 
 def frame_prefix(L, index, W, H, payload_bytes):
@@ -47,6 +48,8 @@ def main():
     ap.add_argument("--quality", type=int, default=12)
     ap.add_argument("--out", default="/tmp/m1_sharded.mpeg")
     ap.add_argument("--verify", action="store_true")
+    ap.add_argument("--peer", action="store_true", help="payloads go to rank 0 through NVLink peer memory (PeerGather)")
+    ap.add_argument("--staged", action="store_true", help="with --peer: local stitch + push kernel instead of a remote stitch")
     a = ap.parse_args()
 
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -58,12 +61,20 @@ def main():
     counts = [frame_range(r, world, a.frames)[1] - frame_range(r, world, a.frames)[0] for r in range(world)]
     enc = M1Encoder(a.width, a.height, 3, MODE_FULL, a.quality, max_frames=max(1, hi - lo), device=local)
     rgb = enc.synth_rgb(12345, lo, max(1, hi - lo), SYNTH_NATURAL)[: hi - lo]      # this rank's pictures
-    res = enc.encode_device(rgb.contiguous()) if hi > lo else enc.alloc_outputs(1)
-    if world > 1:
+    pg = None
+    if world > 1 and a.peer:
+        pg = PeerGather(enc, max(1, max(counts)), slots=1, staged=a.staged)
+        res = pg.batch(0)
+        if hi > lo:
+            enc.encode_device(rgb.contiguous(), res=res)
+        g = pg.finish(0, counts)
+        payloads = g.payloads() if rank == 0 else None
+    elif world > 1:
+        res = enc.encode_device(rgb.contiguous()) if hi > lo else enc.alloc_outputs(1)
         g = gather_to_rank0(res.out, res.frame_bytes, res.frame_offsets, counts)
         payloads = g.payloads() if rank == 0 else None
     else:
-        payloads = res.payloads()
+        payloads = enc.encode_device(rgb.contiguous()).payloads()
 
     ok = True
     if rank == 0:
@@ -85,6 +96,8 @@ def main():
             frames = np.stack([P.synth_rgb(12345, i, a.width, a.height, SYNTH_NATURAL) for i in range(a.frames)])
             ok = open(a.out, "rb").read() == P.encode_stream(frames, a.quality, MODE_FULL)
             print("SHARDED_VERIFY_OK" if ok else "SHARDED_VERIFY_MISMATCH")
+    if pg is not None:
+        pg.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -140,6 +140,26 @@ void  m1cu_pinned_free(void *p);
 int   m1cu_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int   m1cu_memcpy_d2h(void *dst, const void *src, size_t bytes);
 
+/* Peer memory for frame-range sharding (one process per GPU).  The rank that
+ * assembles the stream (rank 0) allocates one receive region per rank with m1cu_device_alloc and
+ * exports it; every other rank opens the handle (peer access over NVLink is enabled on first use)
+ * and passes its region as d_out of m1cu_encode_device, so k_stitch writes the finished payload
+ * bytes straight into rank 0's memory -- no separate gather of the compressed segments.  The
+ * handle is CUDA's 64-byte IPC handle; it is only meaningful to other processes on the same box
+ * (CUDA refuses to open it in the exporting process). */
+#define M1CU_IPC_HANDLE_BYTES 64
+int m1cu_ipc_export(void *d_ptr, unsigned char handle[M1CU_IPC_HANDLE_BYTES]);
+int m1cu_ipc_open(int device, const unsigned char handle[M1CU_IPC_HANDLE_BYTES], void **d_ptr);
+int m1cu_ipc_close(int device, void *d_ptr);
+
+/* Staged variant of the same exchange: copies the payload bytes [0, d_frame_offsets[n_frames]) of a
+ * finished m1cu_encode_device call from d_src to dst (normally a peer mapping from m1cu_ipc_open) with a
+ * small kernel on `stream` (NULL = the context's stream).  On a high-priority side stream it overlaps
+ * the next encode, which a stitch that writes remotely cannot.  The caller orders `stream` after the
+ * encode (event) and before the reuse of d_src. */
+int m1cu_push_payloads(m1cu_ctx *ctx, void *stream, uint8_t *dst, size_t dst_cap, const uint8_t *d_src,
+                       const uint64_t *d_frame_offsets, int n_frames);
+
 #ifdef __cplusplus
 }
 #endif
