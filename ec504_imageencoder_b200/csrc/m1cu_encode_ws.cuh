@@ -136,7 +136,7 @@ k_encode_ws(const __grid_constant__ M1Geom g, const uint8_t *__restrict__ rgb, c
             int v[64];
             mbar_wait(&full[s], ph);
             if (active) {
-                const int key4 = blk_key(pb) << 2;
+                const int key4 = blk_key(pb, C) << 2;
                 const int *src = planes + pb * 64;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {

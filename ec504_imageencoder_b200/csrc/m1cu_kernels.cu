@@ -147,34 +147,50 @@ __host__ __device__ constexpr int zz_raster(int z)
 // -------------------------------------------------------------------------------------------
 // Shared-memory plane layout.  Samples are int32, block-major: block `blk` owns 64 words; its
 // sixteen 16-byte chunks (chunk i = row*2 + (col>>2)) are XOR-swizzled with a per-block key so
-// that both the producers (16x2-pixel colour tiles, 128-bit stores) and the consumers (one thread
+// that both the producers (8x2-pixel colour half-tiles, 128-bit stores) and the consumers (one thread
 // per block, 128-bit loads) are bank-conflict free.
 //   luma blocks:   blk = by * 2C + bc      (by = block row 0/1 of the macroblock row, bc = 8-pixel column)
 //   chroma blocks: blk = 4C + mb (Cb), 5C + mb (Cr)                       C = chunk_mbs
 // Exactly one consumer thread reads each block.  After it has pulled the block into registers it
 // reuses the first 128 bytes of the same 256 bytes for the block's DCT-coefficient record.
+// The key of a block is the low three bits of its position in CODING order (t = 6 * mb + block, the
+// consumer's thread index in k_encode_chunks): eight consecutive consumer threads -- one 128-bit
+// shared-memory wavefront -- then hold eight different keys, and so do eight neighbouring colour
+// strips (block columns 8j .. 8j+7 map to t & 7 = 0,1,6,7,4,5,2,3 (+2 for the lower block row)).
 // -------------------------------------------------------------------------------------------
-__device__ __forceinline__ int blk_key(int blk) { return (blk ^ (blk >> 3)) & 7; }
-__device__ __forceinline__ int chunk_word(int blk, int i)      // first word of chunk i of block blk
+__device__ __forceinline__ int blk_key(int blk, int C)
 {
-    return blk * 64 + (((i & 8) | ((i & 7) ^ blk_key(blk))) << 2);
+    if (blk < 4 * C) {
+        const int by = blk >= 2 * C, bc = blk - by * 2 * C;
+        return (6 * (bc >> 1) + 2 * by + (bc & 1)) & 7;
+    }
+    const int cr = blk >= 5 * C;
+    return (6 * (blk - (4 + cr) * C) + 4 + cr) & 7;
 }
-__device__ __forceinline__ int plane_word(int blk, int r, int c)
+__device__ __forceinline__ int chunk_word_keyed(int blk, int i, int key)      // first word of chunk i of block blk
 {
-    return chunk_word(blk, r * 2 + (c >> 2)) + (c & 3);
+    return blk * 64 + (((i & 8) | ((i & 7) ^ key)) << 2);
+}
+__device__ __forceinline__ int chunk_word(int blk, int i, int C) { return chunk_word_keyed(blk, i, blk_key(blk, C)); }
+__device__ __forceinline__ int plane_word(int blk, int r, int c, int C)
+{
+    return chunk_word(blk, r * 2 + (c >> 2), C) + (c & 3);
 }
 // Coefficient record of thread t: 32 words at byte offset t*256, each holding two BIASED
 // coefficients as 16-bit lanes: word w = (z & 15) + 16*(z >> 5) carries zigzag position z in its low
 // lane when bit 4 of z is clear, in its high lane otherwise (pairs (z, z+16)).  16-byte groups are
-// XOR-swizzled by t.  rec_index returns the index in shorts.
+// XOR-swizzled by `key` (k_encode_chunks: the owning thread's index, see blk_key; the experimental
+// kernels: t itself).  rec_index returns the index in shorts.
 // kStride = distance between records in shorts (128 when the record aliases the block's plane
 // memory, 64 for the dense record array of the warp-specialised kernel).
 template <int kStride = 128>
-__device__ __forceinline__ int rec_index(int t, int z)
+__device__ __forceinline__ int rec_index(int t, int z, int key)
 {
     const int w = (z & 15) + ((z >> 5) << 4);
-    return t * kStride + ((((w >> 2) ^ t) & 7) << 3) + ((w & 3) << 1) + ((z >> 4) & 1);
+    return t * kStride + ((((w >> 2) ^ key) & 7) << 3) + ((w & 3) << 1) + ((z >> 4) & 1);
 }
+template <int kStride = 128>
+__device__ __forceinline__ int rec_index(int t, int z) { return rec_index<kStride>(t, z, t); }
 
 // -------------------------------------------------------------------------------------------
 // Bit sinks for the block coder.
@@ -232,13 +248,14 @@ __device__ __forceinline__ int quant_level(int biased, int z, const M1Tables *tb
 // level is outside the reference's encodable range.
 template <int kStride = 128, class Sink>
 __device__ __forceinline__ int code_block(Sink &s, const short *rec, int tid, unsigned long long nz,
-                                          bool is_luma, const M1Tables *tb)
+                                          bool is_luma, const M1Tables *tb, int key = -1)
 {
+    if (key < 0) key = tid;                                   // record swizzled by its own index
     int bad = 0;
     int prev = -1;
     unsigned long long m = nz;
     if (nz & 1ull) {
-        const int v = quant_level(rec[rec_index<kStride>(tid, 0)], 0, tb);
+        const int v = quant_level(rec[rec_index<kStride>(tid, 0, key)], 0, tb);
         int c = v < 0 ? -v : v;
         const int low = c & 0xff;
         const int sz = low ? 32 - __clz(low) : 1;            // highest set bit of bits 0..7, default 1
@@ -257,7 +274,7 @@ __device__ __forceinline__ int code_block(Sink &s, const short *rec, int tid, un
     while (m) {
         const int k = __ffsll((long long)m) - 1;
         m &= m - 1ull;
-        const int L = quant_level(rec[rec_index<kStride>(tid, k)], k, tb);
+        const int L = quant_level(rec[rec_index<kStride>(tid, k, key)], k, tb);
         const int r = k - prev - 2;                          // run - 1 of source/vlc.c:326
         const int mag = L < 0 ? -L : L;
         const int a = mag - 1;
@@ -334,8 +351,8 @@ __device__ __forceinline__ void convert_half_tile(const HalfTilePixels<CH> px, i
     int sb[4], sr[4];
     // The four 16-byte luma groups of this strip are chunks i0 .. i0+3 of one block (i0 = 4*(qy & 3)):
     // chunk_word(blk, i0 + n) == a1 ^ (n << 2), one LOP3 per store instead of the full swizzle.
-    const int blk = (qy >> 2) * 2 * C + bc, i0 = (qy & 3) << 2;
-    const int a1 = chunk_word(blk, i0);
+    const int by = qy >> 2, blk = by * 2 * C + bc, i0 = (qy & 3) << 2;
+    const int a1 = chunk_word_keyed(blk, i0, (6 * (bc >> 1) + 2 * by + (bc & 1)) & 7);   // == blk_key(blk, C)
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
@@ -354,8 +371,9 @@ __device__ __forceinline__ void convert_half_tile(const HalfTilePixels<CH> px, i
         }
     }
     const int k = bc >> 1, h = bc & 1;                // macroblock, left/right half of its chroma row
-    *(int4 *)(planes + chunk_word(4 * C + k, qy * 2 + h)) = make_int4(sb[0] >> 2, sb[1] >> 2, sb[2] >> 2, sb[3] >> 2);
-    *(int4 *)(planes + chunk_word(5 * C + k, qy * 2 + h)) = make_int4(sr[0] >> 2, sr[1] >> 2, sr[2] >> 2, sr[3] >> 2);
+    const int kc = (6 * k + 4) & 7;                   // key of the Cb block; the Cr block (thread + 1) has kc ^ 1
+    *(int4 *)(planes + chunk_word_keyed(4 * C + k, qy * 2 + h, kc)) = make_int4(sb[0] >> 2, sb[1] >> 2, sb[2] >> 2, sb[3] >> 2);
+    *(int4 *)(planes + chunk_word_keyed(5 * C + k, qy * 2 + h, kc ^ 1)) = make_int4(sr[0] >> 2, sr[1] >> 2, sr[2] >> 2, sr[3] >> 2);
 }
 
 template <int CH>
@@ -380,11 +398,11 @@ __device__ __noinline__ void color_half_tile_generic(const uint8_t *__restrict__
                 int yy, cb, cr;
                 ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
                 const int rr = 2 * qy + dy, cc = 2 * qx + dx;
-                planes[plane_word((rr >> 3) * 2 * C + bc, rr & 7, cc)] = yy;
+                planes[plane_word((rr >> 3) * 2 * C + bc, rr & 7, cc, C)] = yy;
                 sb += cb; sr += cr;
             }
-        planes[plane_word(4 * C + (bc >> 1), qy, 4 * (bc & 1) + qx)] = sb >> 2;
-        planes[plane_word(5 * C + (bc >> 1), qy, 4 * (bc & 1) + qx)] = sr >> 2;
+        planes[plane_word(4 * C + (bc >> 1), qy, 4 * (bc & 1) + qx, C)] = sb >> 2;
+        planes[plane_word(5 * C + (bc >> 1), qy, 4 * (bc & 1) + qx, C)] = sr >> 2;
     }
 }
 
@@ -469,7 +487,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
             const uint8_t *p = fr + ((size_t)(16 * (mb0 + mb) + r) * g.W + x0 + c) * g.channels;
             int yy, cb, cr;
             ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
-            planes[plane_word((r >> 3) * 2 * C + 2 * mb + (c >> 3), r & 7, c & 7)] = yy;
+            planes[plane_word((r >> 3) * 2 * C + 2 * mb + (c >> 3), r & 7, c & 7, C)] = yy;
         }
         const int half = g.W / 2;
         for (int i = tid; i < 64 * nmb; i += nthr) {
@@ -478,8 +496,8 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
             const uint8_t *p = fr + off * g.channels;      // pixel `off` of the row-major picture
             int yy, cb, cr;
             ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
-            planes[plane_word(4 * C + mb, r, c)] = cb;
-            planes[plane_word(5 * C + mb, r, c)] = cr;
+            planes[plane_word(4 * C + mb, r, c, C)] = cb;
+            planes[plane_word(5 * C + mb, r, c, C)] = cr;
         }
     }
     __syncthreads();
@@ -496,7 +514,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     if (active) {
         int v[64];
         {
-            const int key4 = blk_key(pb) << 2;
+            const int key4 = (tid & 7) << 2;                 // == blk_key(pb, C): threads are in coding order
             const int *src = planes + pb * 64;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -532,12 +550,12 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         // the block's samples are in registers now: its 256 bytes of plane become the record
 #pragma unroll
         for (int gI = 0; gI < 8; ++gI)
-            *(uint4 *)(rec + pb * 128 + (((gI ^ pb) & 7) << 3)) =
+            *(uint4 *)(rec + pb * 128 + (((gI ^ tid) & 7) << 3)) =
                 make_uint4(pk[4 * gI], pk[4 * gI + 1], pk[4 * gI + 2], pk[4 * gI + 3]);
 
         // ---- phase 3: code the block into registers ------------------------------------------
         if (blk == 0) acc.put(3u, 2);                       // address increment '1' + macroblock_type '1'
-        if (code_block(acc, rec, pb, nz, is_luma, tb)) atomicOr(err, M1_ERRBIT_LEVEL);
+        if (code_block(acc, rec, pb, nz, is_luma, tb, tid & 7)) atomicOr(err, M1_ERRBIT_LEVEL);
     }
 
     // scan of the block lengths in thread (= coding) order
@@ -558,7 +576,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         for (int i = tid; i < nmb * 384; i += nthr) {
             const int p = i >> 6, z = i & 63, m = p / 6, b = p - m * 6;
             const int t = b < 4 ? (b >> 1) * 2 * C + 2 * m + (b & 1) : b * C + m;
-            dst[i] = (short)quant_level(rec[rec_index(t, z)], z, tb);
+            dst[i] = (short)quant_level(rec[rec_index(t, z, p & 7)], z, tb);   // p = 6 * m + b = the block's thread
         }
     }
 
@@ -595,7 +613,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
             } else {
                 WindowWriter ww{win, my_off, w0, WW};           // long block, or one straddling the window
                 if (blk == 0) ww.put(3u, 2);
-                code_block(ww, rec, pb, nz, is_luma, tb);
+                code_block(ww, rec, pb, nz, is_luma, tb, tid & 7);
             }
         }
         __syncthreads();
