@@ -41,7 +41,8 @@ def _nvcc() -> str:
 
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
-    deps = srcs + [os.path.join(CSRC, h) for h in ("m1cu_common.cuh", "m1cu_kernels.h", "m1cu_tables.h")]
+    deps = srcs + [os.path.join(CSRC, h) for h in ("m1cu_common.cuh", "m1cu_kernels.h", "m1cu_tables.h", "m1cu_block.cuh",
+                                                   "m1cu_quant.h", "m1cu_encode_ws.cuh", "m1cu_encode_persist.cuh")]
     deps.append(os.path.join(ROOT, "include", "m1cu.h"))
     if not force and _newer(LIB_M1CU, deps):
         return LIB_M1CU

@@ -4,6 +4,7 @@
 #include "../../include/m1cu.h"
 #include "m1cu_common.cuh"
 #include "m1cu_kernels.h"
+#include "m1cu_quant.h"
 
 #include <math.h>
 #include <stdio.h>
@@ -81,29 +82,6 @@ int fail(m1cu_ctx *c, int code, const char *what, cudaError_t e = cudaSuccess)
         cudaError_t e_ = (call);                                              \
         if (e_ != cudaSuccess) return fail(ctx, M1CU_ERR_CUDA, #call, e_);    \
     } while (0)
-
-// (c * mul + ((c >> 31) & mask)) >> shift == c / m (C truncation) for |c| <= 2047 ?
-bool make_quant(const int32_t qm[64], M1Quant *q)
-{
-    for (int k = 0; k < 64; ++k) {
-        const int m = qm[k];
-        if (m < 1 || m > 8192) return false;               // packed non-zero test needs 0x7800 - m > 0 with room
-        int fl = 0;
-        while ((2 << fl) <= m) ++fl;                       // floor(log2 m)
-        const int S = 19 + fl;
-        const long long one = 1ll << S;
-        const int K = (int)((one + m - 1) / m);
-        q->mul[k] = K; q->shift[k] = S; q->ta[k] = m - 1; q->tb[k] = 2 * m - 2;
-        for (int c = -2047; c <= 2047; ++c) {
-            const long long prod = (long long)c * K + ((c < 0) ? (one - 1) : 0);
-            if (prod > 0x7fffffffll || prod < -0x80000000ll) return false;
-            const int got = (int)(prod >> S);
-            if (got != c / m) return false;
-            if (((unsigned)(c + q->ta[k]) > (unsigned)q->tb[k]) != (c / m != 0)) return false;
-        }
-    }
-    return true;
-}
 
 cudaEvent_t take_event(m1cu_ctx *ctx)
 {
@@ -219,7 +197,7 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     }
 
     m1cu_qmatrix(quality, ctx->qm);
-    if (!make_quant(ctx->qm, &ctx->q)) { delete ctx; return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: quantiser constants failed self-check"); }
+    if (!m1_make_quant(ctx->qm, &ctx->q)) { delete ctx; return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: quantiser constants failed self-check"); }
 
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(ctx, M1CU_ERR_CUDA, #call, e_); memcpy(g_last_error, ctx->err, sizeof g_last_error); m1cu_destroy(ctx); return rc_; } } while (0)
     CUC(cudaSetDevice(device));

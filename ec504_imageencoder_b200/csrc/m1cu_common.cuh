@@ -41,17 +41,17 @@ struct M1Geom {
     unsigned long long frame_stride;   // input bytes per picture
 };
 
-// Quantiser constants for raster position k: level = (c * mul + ((c >> 31) & ((1 << shift) - 1))) >> shift
-// == C truncating division c / m (source/image_processing.c:367) for |c| <= 2047; checked
-// exhaustively on the host when the context is created.
+// Quantiser constants for raster position k (m1cu_quant.h fills and checks them):
+//   |level| = floor(|c| / m) = high word of (2|c| + 1) * rcp, rcp = ceil(2^31 / m)   (C truncating division
+//   c / m of source/image_processing.c:367 once the sign is put back), exact for |c| <= 2047;
+//   level != 0  <=>  (unsigned)(c + ta) > tb.
 struct M1Quant {
-    int mul[64];
-    int shift[64];
+    uint32_t rcp[64];
     int ta[64];                // m - 1
-    int tb[64];                // 2m - 2 : level != 0  <=>  (unsigned)(c + ta) > tb
+    int tb[64];                // 2m - 2
 };
 
-// Non-zero test constants, one word per coefficient pair (see k_encode_chunks): lanes 0x7800 - m and
+// Non-zero test constants, one word per coefficient pair (see pack_and_flag): lanes 0x7800 - m and
 // 0x8800 - m.  Passed by value as a kernel parameter so that the statically indexed uses read them
 // straight from the constant bank.
 struct M1NzKeys {
@@ -59,10 +59,10 @@ struct M1NzKeys {
 };
 
 struct alignas(16) M1Tables {   // size is a multiple of 16 (copied to shared memory in 128-bit pieces)
-    uint32_t ac[112];
+    uint32_t ac[112];          // (len << 24) | code; entry 0 = '11' (run 0, |level| 1), see code_block
     uint32_t dc[18];
-    uint8_t  first[36];
-    int      qmul[64];         // quantiser constants in ZIGZAG order (for the coder's dynamic index)
-    int      qshift[64];
+    uint16_t acrun[64];        // run r (= zeros - 1): first entry | entries << 8; 0 entries from r = 32 up
+    uint32_t qrcp[64];         // quantiser reciprocals in ZIGZAG order (for the coder's dynamic index)
+    uint8_t  zofs[64];         // byte offset of zigzag position z in an unswizzled coefficient record
     uint32_t ka[32], kb[32];   // per coefficient-pair word: lanes 0x7800 - m and 0x8800 - m (non-zero test)
 };

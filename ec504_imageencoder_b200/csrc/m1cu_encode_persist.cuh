@@ -150,21 +150,7 @@ k_encode_persist(const __grid_constant__ M1Geom g, const uint8_t *__restrict__ r
             }
             fdct8x8(v);
             uint32_t pk[32];
-            uint32_t half[2];
-#pragma unroll
-            for (int hblk = 0; hblk < 2; ++hblk) {
-                uint32_t fl = 0;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int w = hblk * 16 + i, z = hblk * 32 + i;
-                    const uint32_t p = (uint32_t)v[zz_raster(z)] | ((uint32_t)v[zz_raster(z + 16)] << 16);
-                    pk[w] = p;
-                    const uint32_t f = ((p + tb->ka[w]) | (tb->kb[w] - p)) & 0x80008000u;
-                    fl = f + (fl >> 1);
-                }
-                half[hblk] = fl;
-            }
-            nz = ((unsigned long long)half[1] << 32) | half[0];
+                nz = pack_and_flag(v, pk, *tb);
 #pragma unroll
             for (int gI = 0; gI < 8; ++gI)
                 *(uint4 *)(rec + pb * 128 + (((gI ^ pb) & 7) << 3)) =
@@ -172,6 +158,7 @@ k_encode_persist(const __grid_constant__ M1Geom g, const uint8_t *__restrict__ r
             // ---- phase 3: code the block into registers
             if (blk == 0) acc.put(3u, 2);
             if (code_block(acc, rec, pb, nz, is_luma, tb)) atomicOr(err, M1_ERRBIT_LEVEL);
+            acc.finish();
         }
 
         // scan of the block lengths in thread (= coding) order

@@ -154,27 +154,14 @@ k_encode_ws(const __grid_constant__ M1Geom g, const uint8_t *__restrict__ rgb, c
             if (active) {
                 fdct8x8(v);
                 uint32_t pk[32];
-                uint32_t half[2];
-#pragma unroll
-                for (int hblk = 0; hblk < 2; ++hblk) {
-                    uint32_t fl = 0;
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const int wi = hblk * 16 + i, z = hblk * 32 + i;
-                        const uint32_t p = (uint32_t)v[zz_raster(z)] | ((uint32_t)v[zz_raster(z + 16)] << 16);
-                        pk[wi] = p;
-                        const uint32_t f = ((p + tb->ka[wi]) | (tb->kb[wi] - p)) & 0x80008000u;
-                        fl = f + (fl >> 1);
-                    }
-                    half[hblk] = fl;
-                }
-                nz = ((unsigned long long)half[1] << 32) | half[0];
+                nz = pack_and_flag(v, pk, *tb);
 #pragma unroll
                 for (int gI = 0; gI < 8; ++gI)
                     *(uint4 *)(rec + bt * 64 + (((gI ^ bt) & 7) << 3)) =
                         make_uint4(pk[4 * gI], pk[4 * gI + 1], pk[4 * gI + 2], pk[4 * gI + 3]);
                 if (blk == 0) acc.put(3u, 2);                    // address increment '1' + macroblock_type '1'
                 if (code_block<64>(acc, rec, bt, nz, is_luma, tb)) atomicOr(err, M1_ERRBIT_LEVEL);
+                acc.finish();
             }
 
             // scan of the block lengths over the 96 block threads (coding order)

@@ -2,7 +2,8 @@
 // See m1cu_common.cuh for the pipeline and include/m1cu.h for the reference interfaces replaced.
 #include "m1cu_common.cuh"
 #include "m1cu_kernels.h"
-#include "m1cu_tables.h"
+#include "m1cu_block.cuh"
+#include "m1cu_quant.h"
 
 // -------------------------------------------------------------------------------------------
 // Exact colour conversion.  The reference (source/image_processing.c:104-106) evaluates
@@ -58,93 +59,6 @@ __device__ __forceinline__ void ycbcr_from_doubles(double rd, double gd, double 
 }
 
 // -------------------------------------------------------------------------------------------
-// 8-point integer butterfly of fast_DCT (source/image_processing.c:210-238).  On return
-//   t0 = k0 sum, t1 = k4 diff, t2 = k2 (unshifted), t3 = k6 (unshifted),
-//   t4/t5: k1 = t4 + t5, k7 = t4 - t5 (unshifted), t6 -> k3, t7 -> k5 (before the r2 scaling).
-// -------------------------------------------------------------------------------------------
-struct Fdct8 { int t0, t1, t2, t3, t4, t5, t6, t7; };
-
-__device__ __forceinline__ Fdct8 fdct_core(int x0, int x1, int x2, int x3, int x4, int x5, int x6, int x7)
-{
-    const int c1 = 1004, s1 = 200, c3 = 851, s3 = 569, r2c6 = 554, r2s6 = 1337;
-    const int a0 = x0 + x7, d0 = x0 - x7;
-    const int a1 = x1 + x6, d1 = x1 - x6;
-    const int a2 = x2 + x5, d2 = x2 - x5;
-    const int a3 = x3 + x4, d3 = x3 - x4;
-    const int e0 = a0 + a3, e3 = a0 - a3;
-    const int e1 = a1 + a2, e2 = a1 - a2;
-    const int m12 = c1 * (d1 + d2);
-    const int p2 = (-s1 - c1) * d2 + m12;
-    const int p1 = (s1 - c1) * d1 + m12;
-    const int m03 = c3 * (d0 + d3);
-    const int p3 = (-s3 - c3) * d3 + m03;
-    const int p0 = (s3 - c3) * d0 + m03;
-    const int m78 = r2c6 * (e2 + e3);
-    Fdct8 o;
-    o.t0 = e0 + e1;
-    o.t1 = e0 - e1;
-    o.t2 = (r2s6 - r2c6) * e3 + m78;
-    o.t3 = (-r2s6 - r2c6) * e2 + m78;
-    o.t5 = p0 + p2;
-    o.t7 = p0 - p2;
-    o.t4 = p3 + p1;
-    o.t6 = p3 - p1;
-    return o;
-}
-
-// Forward DCT of one 8x8 block held in registers: v[i*8+j] in, dct[u*8+v] + M1_COEF_BIAS out (in
-// place).  Row pass source/image_processing.c:198-250, column pass :253-305.  The bias (2048, folded
-// into the rounding constants of the final shifts, so it is free and exact: (a + b*2^s) >> s ==
-// (a >> s) + b) makes every output a non-negative 12-bit number, which lets two coefficients share a
-// 32-bit word without sign trouble (see the non-zero test in k_encode_chunks).
-#define M1_COEF_BIAS 2048
-__device__ __forceinline__ void fdct8x8(int (&v)[64])
-{
-    const int r2 = 181;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        Fdct8 o = fdct_core(v[i * 8 + 0], v[i * 8 + 1], v[i * 8 + 2], v[i * 8 + 3],
-                            v[i * 8 + 4], v[i * 8 + 5], v[i * 8 + 6], v[i * 8 + 7]);
-        v[i * 8 + 0] = o.t0;
-        v[i * 8 + 4] = o.t1;
-        v[i * 8 + 2] = o.t2 >> 10;
-        v[i * 8 + 6] = o.t3 >> 10;
-        v[i * 8 + 7] = (o.t4 - o.t5) >> 10;
-        v[i * 8 + 1] = (o.t4 + o.t5) >> 10;
-        v[i * 8 + 3] = (o.t6 * r2) >> 17;
-        v[i * 8 + 5] = (o.t7 * r2) >> 17;
-    }
-#pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        Fdct8 o = fdct_core(v[0 * 8 + j], v[1 * 8 + j], v[2 * 8 + j], v[3 * 8 + j],
-                            v[4 * 8 + j], v[5 * 8 + j], v[6 * 8 + j], v[7 * 8 + j]);
-        v[0 * 8 + j] = (o.t0 + (16 + (M1_COEF_BIAS << 3))) >> 3;
-        v[4 * 8 + j] = (o.t1 + (16 + (M1_COEF_BIAS << 3))) >> 3;
-        v[2 * 8 + j] = (o.t2 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
-        v[6 * 8 + j] = (o.t3 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
-        v[7 * 8 + j] = (o.t4 - o.t5 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
-        v[1 * 8 + j] = (o.t4 + o.t5 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
-        v[3 * 8 + j] = ((o.t6 >> 8) * r2 + (8192 + (M1_COEF_BIAS << 12))) >> 12;
-        v[5 * 8 + j] = ((o.t7 >> 8) * r2 + (8192 + (M1_COEF_BIAS << 12))) >> 12;
-    }
-}
-
-// zigzag rank of raster position k (source/image_processing.c:28-37), compile-time table
-__host__ __device__ constexpr int zz_rank(int k)
-{
-    constexpr int t[64] = { 0,  1,  5,  6, 14, 15, 27, 28,  2,  4,  7, 13, 16, 26, 29, 42,
-                            3,  8, 12, 17, 25, 30, 41, 43,  9, 11, 18, 24, 31, 40, 44, 53,
-                           10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60,
-                           21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63 };
-    return t[k];
-}
-__host__ __device__ constexpr int zz_raster(int z)
-{
-    for (int k = 0; k < 64; ++k) if (zz_rank(k) == z) return k;
-    return 0;
-}
-
-// -------------------------------------------------------------------------------------------
 // Shared-memory plane layout.  Samples are int32, block-major: block `blk` owns 64 words; its
 // sixteen 16-byte chunks (chunk i = row*2 + (col>>2)) are XOR-swizzled with a per-block key so
 // that both the producers (8x2-pixel colour half-tiles, 128-bit stores) and the consumers (one thread
@@ -176,43 +90,9 @@ __device__ __forceinline__ int plane_word(int blk, int r, int c, int C)
 {
     return chunk_word(blk, r * 2 + (c >> 2), C) + (c & 3);
 }
-// Coefficient record of thread t: 32 words at byte offset t*256, each holding two BIASED
-// coefficients as 16-bit lanes: word w = (z & 15) + 16*(z >> 5) carries zigzag position z in its low
-// lane when bit 4 of z is clear, in its high lane otherwise (pairs (z, z+16)).  16-byte groups are
-// XOR-swizzled by `key` (k_encode_chunks: the owning thread's index, see blk_key; the experimental
-// kernels: t itself).  rec_index returns the index in shorts.
-// kStride = distance between records in shorts (128 when the record aliases the block's plane
-// memory, 64 for the dense record array of the warp-specialised kernel).
-template <int kStride = 128>
-__device__ __forceinline__ int rec_index(int t, int z, int key)
-{
-    const int w = (z & 15) + ((z >> 5) << 4);
-    return t * kStride + ((((w >> 2) ^ key) & 7) << 3) + ((w & 3) << 1) + ((z >> 4) & 1);
-}
-template <int kStride = 128>
-__device__ __forceinline__ int rec_index(int t, int z) { return rec_index<kStride>(t, z, t); }
-
 // -------------------------------------------------------------------------------------------
-// Bit sinks for the block coder.
+// Shared-memory bit sink for the block coder (the register sink BitAcc is in m1cu_block.cuh).
 // -------------------------------------------------------------------------------------------
-// First 64 bits of a block in registers (typical blocks are 5..40 bits); n keeps counting past 64
-// so the length is always exact, the bits are only valid while n <= 64.
-struct BitAcc {
-    uint32_t hi, lo;
-    int n;
-    __device__ __forceinline__ void put(uint32_t code, int len)
-    {
-        const int end = n + len;
-        if (end <= 32) {
-            hi |= code << (32 - end);
-        } else if (end <= 64) {
-            if (n < 32) hi |= code >> (end - 32);
-            lo |= code << (64 - end);
-        }
-        n = end;
-    }
-};
-
 // Streams MSB-first into a shared-memory window of logical 32-bit words covering chunk bits
 // [w0, w0 + 32*M1_WIN_WORDS); bits outside the window are dropped (another pass takes them).
 struct WindowWriter {
@@ -232,70 +112,6 @@ struct WindowWriter {
         if (lo && word + 1 >= 0 && word + 1 < nw) atomicOr(&win[word + 1], lo);
     }
 };
-
-// quantised level of zigzag position z from the DCT coefficient c: C truncating division by the
-// scaled matrix entry (source/image_processing.c:367), as multiply-shift (see M1Tables).
-__device__ __forceinline__ int quant_level(int biased, int z, const M1Tables *tb)
-{
-    const int c = biased - M1_COEF_BIAS;
-    const int sh = tb->qshift[z];
-    return (c * tb->qmul[z] + ((c >> 31) & ((1 << sh) - 1))) >> sh;
-}
-
-// One block's bits: DC (source/mpeg1_blk.c:67-113), AC walk (source/image_processing.c:400-433,
-// source/vlc.c:315-385), end of block (source/mpeg1_blk.c:115-117).  rec: the shared coefficient
-// records; nz: bit z set <=> quantised level z is non-zero.  Returns non-zero when a coded AC
-// level is outside the reference's encodable range.
-template <int kStride = 128, class Sink>
-__device__ __forceinline__ int code_block(Sink &s, const short *rec, int tid, unsigned long long nz,
-                                          bool is_luma, const M1Tables *tb, int key = -1)
-{
-    if (key < 0) key = tid;                                   // record swizzled by its own index
-    int bad = 0;
-    int prev = -1;
-    unsigned long long m = nz;
-    if (nz & 1ull) {
-        const int v = quant_level(rec[rec_index<kStride>(tid, 0, key)], 0, tb);
-        int c = v < 0 ? -v : v;
-        const int low = c & 0xff;
-        const int sz = low ? 32 - __clz(low) : 1;            // highest set bit of bits 0..7, default 1
-        const uint32_t e = tb->dc[sz + (is_luma ? 0 : 9)];
-        if (v < 0) c ^= 1 << (sz - 1);
-        const uint32_t val = (uint32_t)c & ((1u << sz) - 1u);
-        s.put(((e & 0xffffffu) << sz) | val, (int)(e >> 24) + sz);
-        prev = 0;
-        m &= ~1ull;
-    } else {
-        if (is_luma) s.put(4u, 3); else s.put(0u, 2);
-    }
-    // coding stops at the first non-zero whose predecessor position is also non-zero
-    const unsigned long long adj = nz & (nz << 1);
-    if (adj) m &= (adj & (0ull - adj)) - 1ull;
-    while (m) {
-        const int k = __ffsll((long long)m) - 1;
-        m &= m - 1ull;
-        const int L = quant_level(rec[rec_index<kStride>(tid, k, key)], k, tb);
-        const int r = k - prev - 2;                          // run - 1 of source/vlc.c:326
-        const int mag = L < 0 ? -L : L;
-        const int a = mag - 1;
-        prev = k;
-        if (r == 0 && a == 0) { s.put(3u, 2); continue; }
-        if (r <= 31) {
-            const int f = tb->first[r];
-            if (a < (int)tb->first[r + 1] - f) {
-                const uint32_t e = tb->ac[f + a];
-                s.put(e & 0xffffffu, (int)(e >> 24));
-                continue;
-            }
-        }
-        if (mag >= 256) bad = 1;                             // reference: NULL -> crash
-        const uint32_t head = (1u << 6) | (uint32_t)(r & 0x3f);    // 000001 rrrrrr
-        if (mag < 128) s.put((head << 8) | ((uint32_t)L & 0xffu), 20);
-        else           s.put((head << 16) | (L < 0 ? 0x8000u : 0u) | ((uint32_t)L & 0xffu), 28);
-    }
-    s.put(2u, 2);
-    return bad;
-}
 
 // -------------------------------------------------------------------------------------------
 // Colour tiles.
@@ -526,27 +342,9 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
             }
         }
         fdct8x8(v);
-        // Pack pairs (z, z+16) of biased coefficients and test both lanes at once:
-        //   lane + (0x7800 - m) has bit 15 set  <=>  c >=  m
-        //   (0x8800 - m) - lane has bit 15 set  <=>  c <= -m          (m = scaled matrix entry, no
-        // carries cross the lanes: every lane value stays inside [0, 0xffff]), so level != 0 <=> either.
-        // Shifting the accumulator right once per word lands word i's flags on bits i and 16+i.
+        // packed coefficient pairs + the zigzag-order non-zero mask (m1cu_block.cuh)
         uint32_t pk[32];
-        uint32_t half[2];
-#pragma unroll
-        for (int hblk = 0; hblk < 2; ++hblk) {
-            uint32_t fl = 0;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const int w = hblk * 16 + i, z = hblk * 32 + i;
-                const uint32_t p = (uint32_t)v[zz_raster(z)] | ((uint32_t)v[zz_raster(z + 16)] << 16);
-                pk[w] = p;
-                const uint32_t f = ((p + nk.ka[w]) | (nk.kb[w] - p)) & 0x80008000u;
-                fl = f + (fl >> 1);
-            }
-            half[hblk] = fl;
-        }
-        nz = ((unsigned long long)half[1] << 32) | half[0];
+        nz = pack_and_flag(v, pk, nk);
         // the block's samples are in registers now: its 256 bytes of plane become the record
 #pragma unroll
         for (int gI = 0; gI < 8; ++gI)
@@ -554,8 +352,9 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                 make_uint4(pk[4 * gI], pk[4 * gI + 1], pk[4 * gI + 2], pk[4 * gI + 3]);
 
         // ---- phase 3: code the block into registers ------------------------------------------
-        if (blk == 0) acc.put(3u, 2);                       // address increment '1' + macroblock_type '1'
+        if (blk == 0) { acc.lo = 3u; acc.n = 2; }           // address increment '1' + macroblock_type '1'
         if (code_block(acc, rec, pb, nz, is_luma, tb, tid & 7)) atomicOr(err, M1_ERRBIT_LEVEL);
+        acc.finish();
     }
 
     // scan of the block lengths in thread (= coding) order
@@ -834,8 +633,6 @@ __global__ void k_synth_rgb(uint32_t seed, long first_frame, int n_frames, int W
 // -------------------------------------------------------------------------------------------
 // Launchers (called from m1cu_api.cu).
 // -------------------------------------------------------------------------------------------
-void m1k_nz_keys(const M1Quant &q, M1NzKeys *k);
-
 size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
 {
     (void)threads;
@@ -957,25 +754,4 @@ cudaError_t m1k_launch_synth(uint32_t seed, long first_frame, int n_frames, int 
 {
     k_synth_rgb<<<148 * 8, 256, 0, st>>>(seed, first_frame, n_frames, W, H, kind, rgb);
     return cudaGetLastError();
-}
-
-void m1k_nz_keys(const M1Quant &q, M1NzKeys *k)
-{
-    for (int w = 0; w < 32; ++w) {
-        const int zlo = (w & 15) + ((w >> 4) << 5), zhi = zlo + 16;
-        const uint32_t mlo = (uint32_t)q.ta[zz_raster(zlo)] + 1u, mhi = (uint32_t)q.ta[zz_raster(zhi)] + 1u;
-        k->ka[w] = ((0x7800u - mhi) << 16) | (0x7800u - mlo);
-        k->kb[w] = ((0x8800u - mhi) << 16) | (0x8800u - mlo);
-    }
-}
-
-void m1k_fill_tables(M1Tables *t, const M1Quant &q)
-{
-    for (int i = 0; i < 112; ++i) t->ac[i] = i < M1_AC_ENTRIES ? kM1AcTable[i] : 0u;
-    for (int i = 0; i < 18; ++i) t->dc[i] = kM1DcSize[i];
-    for (int i = 0; i < 36; ++i) t->first[i] = i < 33 ? kM1AcFirst[i] : 0;
-    for (int z = 0; z < 64; ++z) { t->qmul[z] = q.mul[zz_raster(z)]; t->qshift[z] = q.shift[zz_raster(z)]; }
-    M1NzKeys nk;
-    m1k_nz_keys(q, &nk);
-    for (int w = 0; w < 32; ++w) { t->ka[w] = nk.ka[w]; t->kb[w] = nk.kb[w]; }
 }

@@ -5,7 +5,7 @@
 size_t      m1k_encode_smem_bytes(const M1Geom &g, int threads);
 int         m1k_encode_threads(const M1Geom &g);
 cudaError_t m1k_prepare(const M1Geom &g);
-void        m1k_fill_tables(M1Tables *t, const M1Quant &q);
+// (m1k_fill_tables / m1_make_quant: inline in m1cu_quant.h)
 
 cudaError_t m1k_launch_encode(const M1Geom &g, const M1Quant &q, const uint8_t *rgb, int n_frames,
                               const M1Tables *tables, uint32_t *staging, uint32_t *chunk_bits,

@@ -1,0 +1,206 @@
+"""The kernels' per-block device functions, compiled for the HOST (tests/host/block_host.cu includes
+ec504_imageencoder_b200/csrc/m1cu_block.cuh unchanged), against the oracle block by block:
+forward DCT (source/image_processing.c:192-307), quantised zigzag levels (:349-381), and the
+block's bits (source/mpeg1_blk.c:67-117, source/image_processing.c:400-433, source/vlc.c:315-385),
+including the register bit accumulator the kernel actually uses for blocks of up to 64 bits.
+
+This runs without a GPU; it checks the arithmetic the GPU parity tests check again end to end.
+"""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "host", "block_host.cu")
+OUT = os.path.join(ROOT, "tests", "_build", "libm1blockhost.so")
+CSRC = os.path.join(ROOT, "ec504_imageencoder_b200", "csrc")
+
+
+def _build():
+    deps = [SRC] + [os.path.join(CSRC, f) for f in ("m1cu_block.cuh", "m1cu_quant.h", "m1cu_common.cuh", "m1cu_tables.h")]
+    if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in deps):
+        return OUT
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("nvcc not available")
+    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
+                    "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC], check=True)
+    return OUT
+
+
+@pytest.fixture(scope="module")
+def bh():
+    lib = C.CDLL(_build())
+    lib.m1bh_set_matrix.restype = C.c_int
+    lib.m1bh_set_matrix.argtypes = [C.c_void_p]
+    lib.m1bh_block.restype = C.c_int
+    lib.m1bh_block.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_char_p, C.c_int, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32),
+                               C.POINTER(C.c_int), C.POINTER(C.c_ulonglong), C.POINTER(C.c_int)]
+    lib.m1bh_code_levels.restype = C.c_int
+    lib.m1bh_code_levels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_int,
+                                     C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_int),
+                                     C.POINTER(C.c_int)]
+    return lib
+
+
+def code_levels(lib, zz, is_luma, tid=11, key=5):
+    zz = np.ascontiguousarray(zz, np.int32).reshape(64)
+    buf = C.create_string_buffer(4096)
+    hi, lo, n, bad = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_int()
+    cnt = lib.m1bh_code_levels(zz.ctypes.data, int(is_luma), tid, key, buf, 4096,
+                               C.byref(hi), C.byref(lo), C.byref(n), C.byref(bad))
+    assert cnt > 0, cnt
+    bits = buf.raw[:cnt].decode()
+    assert n.value == cnt
+    if cnt <= 64:
+        assert f"{(hi.value << 32) | lo.value:064b}"[:cnt] == bits
+    return bits, bad.value
+
+
+def run_block(lib, samples, is_luma, first, tid, key):
+    s = np.ascontiguousarray(samples, np.int32).reshape(64)
+    dct = np.zeros(64, np.int32)
+    lev = np.zeros(64, np.int16)
+    buf = C.create_string_buffer(4096)
+    hi, lo, n, nz, bad = C.c_uint32(), C.c_uint32(), C.c_int(), C.c_ulonglong(), C.c_int()
+    cnt = lib.m1bh_block(s.ctypes.data, int(is_luma), int(first), tid, key, dct.ctypes.data, lev.ctypes.data,
+                         buf, 4096, C.byref(hi), C.byref(lo), C.byref(n), C.byref(nz), C.byref(bad))
+    assert 0 < cnt <= 4096
+    return dct, lev, buf.raw[:cnt].decode(), (hi.value, lo.value, n.value), nz.value, bad.value
+
+
+def blocks(rng, n):
+    """A mix of block statistics: flat, smooth ramps, ramps + noise, uniform noise, extremes."""
+    out = []
+    yy, xx = np.mgrid[0:8, 0:8]
+    for i in range(n):
+        kind = i % 6
+        if kind == 0:
+            b = np.full((8, 8), rng.integers(0, 256))
+        elif kind == 1:
+            b = rng.integers(0, 200) + xx * rng.integers(-6, 7) + yy * rng.integers(-6, 7)
+        elif kind == 2:
+            b = rng.integers(40, 200) + xx * rng.integers(-4, 5) + yy * rng.integers(-4, 5) + rng.integers(0, 16, (8, 8))
+        elif kind == 3:
+            b = rng.integers(0, 256, (8, 8))
+        elif kind == 4:
+            b = np.where(rng.integers(0, 2, (8, 8)) > 0, 255, 0)        # extreme edges
+        else:
+            b = 128 + rng.integers(-3, 4, (8, 8))
+        out.append(np.clip(b, 0, 255).astype(np.uint8).reshape(64))
+    return out
+
+
+@pytest.mark.parametrize("quality", [1, 5, 12, 50, 75, 89])
+def test_block_functions_match_oracle(bh, port, quality):
+    qm = port.qmatrix(quality)
+    assert bh.m1bh_set_matrix(qm.ctypes.data) == 0
+    rng = np.random.default_rng(1000 + quality)
+    for i, blk in enumerate(blocks(rng, 1500)):
+        is_luma, first = bool(i & 1), (i % 6 == 0)
+        tid, key = int(rng.integers(0, 96)), int(rng.integers(0, 8))
+        dct, lev, bits, (hi, lo, n), nz, bad = run_block(bh, blk, is_luma, first, tid, key)
+        ref_dct = port.fdct8x8(blk)
+        assert np.array_equal(dct, ref_dct), f"DCT differs on block {i}"
+        ref_zz = port.quant_zigzag(ref_dct, qm)
+        assert np.array_equal(lev.astype(np.int32), ref_zz), f"levels differ on block {i}"
+        assert nz == sum(1 << z for z in range(64) if ref_zz[z] != 0), f"non-zero mask differs on block {i}"
+        ref_bits = ("11" if first else "") + port.block_bits(ref_zz, is_luma)
+        assert bits == ref_bits, f"bits differ on block {i}"
+        assert bad == 0
+        assert n == len(ref_bits)
+        if n <= 64:                                   # the register accumulator holds the whole block
+            acc = f"{(hi << 32) | lo:064b}"[:n]
+            assert acc == ref_bits, f"register accumulator differs on block {i}"
+
+
+def test_quantiser_reciprocals_every_quality(bh, port):
+    """m1_make_quant's exhaustive self-check (|c| <= 2047) passes for every quality factor."""
+    for q in range(1, 101):
+        qm = port.qmatrix(q)
+        assert bh.m1bh_set_matrix(qm.ctypes.data) == 0, f"quality {q}"
+
+
+def test_synthetic_levels_escape_and_runs(bh, port):
+    """Hand-built coefficient patterns through the coder alone are covered by feeding blocks whose
+    DCT is known: a single bright pixel spreads energy over all 64 positions (long runs of coded
+    coefficients, escapes at low quantisers)."""
+    qm = port.qmatrix(89)
+    assert bh.m1bh_set_matrix(qm.ctypes.data) == 0
+    for pos in range(64):
+        for amp in (255, 128, 17):
+            blk = np.zeros(64, np.uint8)
+            blk[pos] = amp
+            dct, lev, bits, acc, nz, bad = run_block(bh, blk, True, False, 7, 3)
+            ref_zz = port.quant_zigzag(port.fdct8x8(blk), qm)
+            assert np.array_equal(lev.astype(np.int32), ref_zz)
+            assert bits == port.block_bits(ref_zz, True)
+
+
+def _zz(pairs):
+    zz = np.zeros(64, np.int32)
+    for z, L in pairs:
+        zz[z] = L
+    return zz
+
+
+def test_coder_known_answers(bh, port):
+    """known-answer bit strings extracted from the reference."""
+    assert bh.m1bh_set_matrix(port.qmatrix(100).ctypes.data) == 0      # all-ones matrix: coefficient = level
+    kats = [
+        (_zz([(0, 5), (2, 3), (3, 2), (6, -1)]), True, "101101000011010"),
+        (_zz([(2, 3)]), True, "1000010010110"),
+        (_zz([(2, 3)]), False, "000010010110"),
+        (_zz([(0, -3)]), True, "010110"),
+        (_zz([]), True, "10010"),
+        (_zz([]), False, "0010"),
+        (_zz([(0, 61), (2, -2), (5, 1)]), True, "111101111010010101110"),
+        (_zz([(0, 255)]), True, "11111101111111110"),
+        (_zz([(0, 256)]), True, "00010"),
+    ]
+    for zz, luma, want in kats:
+        assert port.block_bits(zz, luma) == want
+        assert code_levels(bh, zz, luma)[0] == want
+
+
+def test_coder_random_sparse_levels(bh, port):
+    """Random sparse level patterns incl. long runs, escapes (20- and 28-bit), both signs, DC sizes,
+    blocks longer than 64 bits; the coder stops at the first adjacent pair like the reference."""
+    assert bh.m1bh_set_matrix(port.qmatrix(100).ctypes.data) == 0
+    rng = np.random.default_rng(77)
+    long_blocks = escapes = 0
+    for i in range(6000):
+        zz = np.zeros(64, np.int32)
+        if rng.random() < 0.7:
+            zz[0] = int(rng.integers(-300, 301))
+        pos = 0
+        while True:
+            pos += int(rng.choice([1, 2, 2, 3, 3, 4, 6, 9, 17, 34]))
+            if pos > 63:
+                break
+            mag = int(rng.choice([1, 1, 1, 2, 2, 3, 5, 9, 17, 39, 40, 41, 127, 128, 200, 255]))
+            zz[pos] = mag if rng.random() < 0.5 else -mag
+            if rng.random() < 0.15:
+                break
+        want = port.block_bits(zz, bool(i & 1))
+        got, bad = code_levels(bh, zz, bool(i & 1), tid=int(rng.integers(0, 96)), key=int(rng.integers(0, 8)))
+        assert got == want, (i, zz.tolist())
+        assert bad == 0
+        long_blocks += len(want) > 64
+        escapes += "000001" in want
+    assert long_blocks > 100 and escapes > 100
+
+
+def test_coder_flags_unencodable_level(bh, port):
+    """|coded AC level| >= 256: the reference dereferences NULL (source/vlc.c:383); the kernel flags it."""
+    assert bh.m1bh_set_matrix(port.qmatrix(100).ctypes.data) == 0
+    assert code_levels(bh, _zz([(0, 3), (2, 256)]), True)[1] == 1
+    assert code_levels(bh, _zz([(0, 3), (2, 255)]), True)[1] == 0
+    # ... but not when the coefficient sits behind the stop point and is never coded
+    assert code_levels(bh, _zz([(0, 3), (1, 1), (5, 300)]), True)[1] == 0
