@@ -43,11 +43,14 @@ __device__ __forceinline__ double byte_to_double(uint32_t w, int b)   // b is a 
 // constant-bank operands instead of re-materialising 64-bit immediates through uniform registers.
 __constant__ double kYcc[7] = { 0.299, 0.587, 0.114, 0.168736, 0.331264, 0.418688, 0.081312 };
 
-__device__ __forceinline__ void ycbcr_from_doubles(double rd, double gd, double bd, int &y, int &cb, int &cr)
+__device__ __forceinline__ int luma_from_doubles(double rd, double gd, double bd)
 {
     double t = __dadd_rn(__dmul_rn(kYcc[0], rd), __dmul_rn(kYcc[1], gd));
     t = __dadd_rn(t, __dmul_rn(kYcc[2], bd));
-    y = trunc_nonneg(t);
+    return trunc_nonneg(t);
+}
+__device__ __forceinline__ void chroma_from_doubles(double rd, double gd, double bd, int &cb, int &cr)
+{
     double u = __dsub_rn(128.0, __dmul_rn(kYcc[3], rd));
     u = __dsub_rn(u, __dmul_rn(kYcc[4], gd));
     u = __fma_rn(0.5, bd, u);
@@ -56,6 +59,11 @@ __device__ __forceinline__ void ycbcr_from_doubles(double rd, double gd, double 
     v = __dsub_rn(v, __dmul_rn(kYcc[5], gd));
     v = __dsub_rn(v, __dmul_rn(kYcc[6], bd));
     cr = trunc_nonneg(v);
+}
+__device__ __forceinline__ void ycbcr_from_doubles(double rd, double gd, double bd, int &y, int &cb, int &cr)
+{
+    y = luma_from_doubles(rd, gd, bd);
+    chroma_from_doubles(rd, gd, bd, cb, cr);
 }
 
 // -------------------------------------------------------------------------------------------

@@ -204,3 +204,4 @@ def test_coder_flags_unencodable_level(bh, port):
     assert code_levels(bh, _zz([(0, 3), (2, 255)]), True)[1] == 0
     # ... but not when the coefficient sits behind the stop point and is never coded
     assert code_levels(bh, _zz([(0, 3), (1, 1), (5, 300)]), True)[1] == 0
+
