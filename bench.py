@@ -350,6 +350,8 @@ def run_ours(args):
                          "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": alg_bytes_frame, "frames_per_launch": frames_per_launch,
                          "launch_ms": enc_launch_ms,
+                         "note": ("the dominant kernel is not HBM-bound: it sits at the issue ceiling of its mix of two-cycle "
+                                  "FP64 / ALU / IMAD instructions (DESIGN.md section 7, profiles/r1s2_ubench_issue_mix.txt)"),
                          "kernel_ms_per_step": {"k_encode_chunks": kms[0] / args.steps, "k_layout": kms[1] / args.steps,
                                                 "k_stitch": kms[2] / args.steps}},
         }
