@@ -259,7 +259,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS + 4);         // 16-byte aligned
     int *wtot = (int *)(tb + 1);                                 // [8] bits per warp, 16-byte aligned
 
-    // Per-CTA prologue, kept short: the coder's tables up to qshift[] in 128-bit pieces (the non-zero
+    // Per-CTA prologue, kept short: the coder's tables up to zofs[] in 128-bit pieces (the non-zero
     // keys come from the constant bank), and only the first blockDim.x window words zeroed -- a chunk
     // that needs more (> 32 * blockDim.x bits) zeroes the rest once its size is known.
     constexpr int kTabVecs = ((int)offsetof(M1Tables, ka) + 15) / 16;

@@ -9,7 +9,7 @@
 #define ITERS 2048
 #define CH 8
 
-enum { F64 = 1, ALU = 2, IMA = 4, I2F = 8, IDP = 16, WID = 32, MHI = 64 };
+enum { F64 = 1, ALU = 2, IMA = 4, I2F = 8, IDP = 16, WID = 32, MHI = 64, I2B = 128, MAG = 256 };
 
 template <int M>
 __global__ void k(long long *cycles, double *sinkd, int *sinki, double seed, int iseed)
@@ -36,6 +36,14 @@ __global__ void k(long long *cycles, double *sinkd, int *sinki, double seed, int
             if (M & IDP) asm volatile("dp2a.lo.u32.u32 %0, %1, %2, %0;" : "+r"(p[i]) : "r"(x), "r"(it));
             if (M & WID) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(w[i]) : "r"(x), "r"(it));
             if (M & MHI) asm volatile("mul.hi.u32 %0, %0, %1;" : "+r"(h[i]) : "r"(0xfffffff1u));
+            if (M & I2B) {      // the kernel's conversion: I2F.F64.U8 with a byte selector (byte 1, 2 or 3 of the word)
+                double t; const unsigned sh = (unsigned)c[i] >> (8 * (1 + i % 3));
+                asm volatile("cvt.rn.f64.u8 %0, %1;" : "=d"(t) : "r"(sh)); c[i] = (__double2loint(t) + c[i]) | 0x01010101;
+            }
+            if (M & MAG) {      // the 2^52 alternative: byte extract + DADD
+                const double t = __hiloint2double(0x43300000, (c[i] >> (8 * (1 + i % 3))) & 0xff) - 4503599627370496.0;
+                c[i] = (__double2loint(t) + c[i]) | 0x01010101;
+            }
         }
     }
     const long long t1 = clock64();
@@ -51,7 +59,7 @@ template <int M>
 void row(const char *name)
 {
     int nops = 0;
-    for (int b = 1; b <= MHI; b <<= 1) nops += (M & b) ? 1 : 0;
+    for (int b = 1; b <= MAG; b <<= 1) nops += (M & b) ? 1 : 0;
     printf("%-24s", name);
     for (int wps = 1; wps <= 8; wps *= 2) {
         const int threads = 128 * wps, blocks = 148;
@@ -81,6 +89,9 @@ int main()
     row<F64 | ALU | IMA>("DADD + LOP3 + IMAD");
     row<I2F>("I2F.F64.U32");
     row<I2F | F64>("I2F.F64.U32 + DADD");
+    row<I2B>("I2F.F64.U8.Bn (+IADD+LOP)");
+    row<I2B | F64>("I2F.F64.U8.Bn + DADD");
+    row<MAG>("PRMT+DADD magic (+2)");
     row<IDP>("IDP.2A");
     row<WID>("IMAD.WIDE");
     row<MHI>("IMAD.HI");
