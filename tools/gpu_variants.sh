@@ -10,7 +10,7 @@ for spec in "$@"; do
     python - "$spec" "$v" <<'PY'
 import json, sys
 d = json.load(open('gpurun_out/var_%s.json' % sys.argv[2]))
-print(sys.argv[1], 'fps', round(d['value']), 'ms/step', round(d['ms_per_step'], 3), round(d['roofline']['kernel_ms_per_step']['k_encode_chunks'], 4))
+print(sys.argv[1], 'fps', round(d['value']), 'ms/step', round(d['ms_per_step'], 3), {k: round(v, 4) for k, v in d['roofline']['kernel_ms_per_step'].items()})
 PY
   done
 done
