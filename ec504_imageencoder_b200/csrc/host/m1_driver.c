@@ -71,6 +71,15 @@ static void frame_prefix(long index, int width, int height, int mode, long paylo
     out[5] = (uint8_t)(fwd & 0xff);
 }
 
+void m1_stream_templates(int width, int height, int mode, unsigned char prefix256[256 * 44],
+                         unsigned char prologue[27], unsigned char trailer[4])
+{
+    for (long i = 0; i < 256; ++i) frame_prefix(i, width, height, mode, 0, prefix256 + 44 * i);
+    mpeg1_file_header(2202035, prologue);                 /* include/encoder.h:86 */
+    mpeg1_sys_header(2202035, 0xe6, prologue + 12);       /* :88 */
+    mpeg1_sequence_end(trailer);                          /* see encode_batch */
+}
+
 typedef int (*sink_fn)(void *cookie, const void *data, size_t n);
 
 static int sink_file(void *cookie, const void *data, size_t n) { return fwrite(data, 1, n, (FILE *)cookie) == n ? 0 : -1; }

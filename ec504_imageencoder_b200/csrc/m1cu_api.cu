@@ -40,6 +40,10 @@ struct m1cu_ctx {
     // device state
     uint32_t *d_staging = nullptr, *d_chunk_bits = nullptr, *d_chunk_dst = nullptr;
     M1Tables *d_tables = nullptr;
+    // m1cu_assemble_stream: prefix templates (256 x 44) + prologue (27) on the device, the host copy they came from
+    uint8_t *d_stream_tmpl = nullptr;
+    unsigned long long *d_seg_off = nullptr; int seg_frames = 0;
+    std::vector<uint8_t> h_stream_tmpl;
     int *d_err = nullptr;
     unsigned long long *d_running = nullptr;
     unsigned int *d_done = nullptr;
@@ -235,7 +239,7 @@ int m1cu_destroy(m1cu_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_staging); cudaFree(ctx->d_chunk_bits); cudaFree(ctx->d_chunk_dst);
-    cudaFree(ctx->d_tables); cudaFree(ctx->d_err); cudaFree(ctx->d_running); cudaFree(ctx->d_done);
+    cudaFree(ctx->d_tables); cudaFree(ctx->d_stream_tmpl); cudaFree(ctx->d_seg_off); cudaFree(ctx->d_err); cudaFree(ctx->d_running); cudaFree(ctx->d_done);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_fbytes); cudaFree(ctx->d_foff);
     cudaFree(ctx->d_levels);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -597,6 +601,47 @@ int m1cu_push_payloads(m1cu_ctx *ctx, void *stream, uint8_t *dst, size_t dst_cap
     CU(m1k_launch_push(dst, d_src, (const unsigned long long *)d_frame_offsets + n_frames, (unsigned long long)dst_cap,
                        stream ? (cudaStream_t)stream : ctx->stream));
     ctx->launches += 1;
+    return M1CU_OK;
+}
+
+int m1cu_assemble_stream(m1cu_ctx *ctx, const uint8_t *d_payloads, const uint32_t *d_frame_bytes,
+                         const uint64_t *d_frame_offsets, int n_frames, long first_frame_index,
+                         const uint8_t *h_prefix256, const uint8_t *h_prologue, const uint8_t h_trailer[4],
+                         uint8_t *d_stream, size_t stream_cap, uint64_t *d_stream_bytes)
+{
+    if (!ctx || !d_payloads || !d_frame_bytes || !d_frame_offsets || n_frames <= 0 || !h_prefix256 || !h_trailer ||
+        !d_stream || !d_stream_bytes || ((uintptr_t)d_stream & 15) || ((uintptr_t)d_payloads & 15))
+        return fail(ctx, M1CU_ERR_ARG, "m1cu_assemble_stream: bad argument");
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    constexpr size_t kTmpl = 256 * 44, kAll = kTmpl + 32;           // templates, then the prologue (27 of 32 bytes)
+    if (!ctx->d_stream_tmpl) CU(cudaMalloc(&ctx->d_stream_tmpl, kAll));
+    std::vector<uint8_t> want(kAll, 0);
+    memcpy(want.data(), h_prefix256, kTmpl);
+    if (h_prologue) memcpy(want.data() + kTmpl, h_prologue, 27);
+    if (want != ctx->h_stream_tmpl) {                                // first call, or the caller changed the headers
+        CU(cudaStreamSynchronize(st));                               // nobody reads the old templates any more
+        CU(cudaMemcpy(ctx->d_stream_tmpl, want.data(), kAll, cudaMemcpyHostToDevice));
+        ctx->h_stream_tmpl.swap(want);
+    }
+    if (ctx->seg_frames < n_frames + 1) {
+        CU(cudaStreamSynchronize(st));
+        cudaFree(ctx->d_seg_off); ctx->d_seg_off = nullptr; ctx->seg_frames = 0;
+        CU(cudaMalloc(&ctx->d_seg_off, sizeof(unsigned long long) * (size_t)(n_frames + 1)));
+        ctx->seg_frames = n_frames + 1;
+    }
+    unsigned long long base = 0;
+    if (h_prologue) {
+        if (stream_cap < 27) return fail(ctx, M1CU_ERR_CAPACITY, "m1cu_assemble_stream: stream_cap too small");
+        CU(cudaMemcpyAsync(d_stream, ctx->d_stream_tmpl + kTmpl, 27, cudaMemcpyDeviceToDevice, st));
+        base = 27;
+    }
+    const uint32_t trailer_be = ((uint32_t)h_trailer[0] << 24) | ((uint32_t)h_trailer[1] << 16) | ((uint32_t)h_trailer[2] << 8) | h_trailer[3];
+    CU(m1k_launch_stream(d_payloads, d_frame_bytes, (const unsigned long long *)d_frame_offsets, n_frames, first_frame_index,
+                         ctx->d_stream_tmpl, trailer_be, base, ctx->d_seg_off, d_stream, (unsigned long long)stream_cap,
+                         ctx->d_err, st));
+    CU(cudaMemcpyAsync(d_stream_bytes, ctx->d_seg_off + n_frames, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+    ctx->launches += 2;
     return M1CU_OK;
 }
 

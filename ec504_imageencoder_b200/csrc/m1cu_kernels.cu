@@ -610,6 +610,92 @@ k_push_bytes(uint4 *__restrict__ dst, const uint4 *__restrict__ src, const unsig
         dst[i] = src[i];
 }
 
+// -------------------------------------------------------------------------------------------
+// Final stream image on the device: [prologue] + per picture { 44-byte prefix with the
+// packet length patched in (include/encoder.h:448-454), payload, 4-byte trailer }.  The prefix bytes
+// themselves are built on the host by the reference-API header writers (include/mpeg1_enc.h) and passed
+// in as 256 templates indexed by (picture index & 255) -- the reference's clock is a uint8_t hour.
+//   k_stream_offsets  one CTA: exclusive scan of (48 + payload bytes) -> start of every picture's segment
+//   k_stream_copy     blockIdx.y = picture; aligned 32-bit words of the destination are assembled from two
+//                     source words, the ragged first / last bytes of a segment are written bytewise
+// -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_stream_offsets(int n_frames, const uint32_t *__restrict__ frame_bytes, unsigned long long base,
+                 unsigned long long *__restrict__ seg_off, unsigned long long cap, int *err)
+{
+    __shared__ unsigned long long wsum[32];
+    __shared__ unsigned long long carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) carry = base;
+    __syncthreads();
+    for (int f0 = 0; f0 < n_frames; f0 += 1024) {
+        const int f = f0 + tid;
+        const unsigned long long sz = f < n_frames ? 48ull + frame_bytes[f] : 0ull;
+        unsigned long long incl = sz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        unsigned long long before = carry;
+        for (int w = 0; w < warp; ++w) before += wsum[w];
+        if (f < n_frames) seg_off[f] = before + incl - sz;
+        __syncthreads();
+        if (tid == 1023) carry = before + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        seg_off[n_frames] = carry;
+        if (carry > cap) atomicOr(err, M1_ERRBIT_CAPACITY);
+    }
+}
+
+// byte k of picture f's segment
+__device__ __forceinline__ uint32_t stream_byte(unsigned int k, unsigned int n, const uint8_t *__restrict__ prefix,
+                                                const uint8_t *__restrict__ payload, uint32_t trailer_be)
+{
+    if (k < 44u) {
+        const unsigned int len = (44u + n - 8u) & 0xffffu;          // unsigned short arithmetic of the reference
+        return k == 4u ? len >> 8 : k == 5u ? len & 0xffu : prefix[k];
+    }
+    if (k < 44u + n) return payload[k - 44u];
+    return (trailer_be >> (8u * (3u - (k - 44u - n)))) & 0xffu;
+}
+
+__global__ void __launch_bounds__(256)
+k_stream_copy(const uint8_t *__restrict__ payloads, const uint32_t *__restrict__ frame_bytes,
+              const unsigned long long *__restrict__ frame_off, const unsigned long long *__restrict__ seg_off,
+              long first_index, const uint8_t *__restrict__ prefix256, uint32_t trailer_be,
+              uint8_t *__restrict__ out, unsigned long long cap)
+{
+    const int f = blockIdx.y;
+    const unsigned long long s0 = seg_off[f], s1 = seg_off[f + 1];
+    if (s1 > cap) return;                                            // flagged by k_stream_offsets
+    const unsigned int n = frame_bytes[f];
+    const uint8_t *payload = payloads + frame_off[f];                // 16-byte aligned
+    const uint8_t *prefix = prefix256 + 44u * (unsigned int)((first_index + f) & 255);
+    // destination words fully inside the payload part: [a0, a1) in bytes, both multiples of 4
+    const unsigned long long p0 = s0 + 44ull, p1 = p0 + n;
+    const unsigned long long a0 = (p0 + 3ull) & ~3ull, a1 = p1 & ~3ull;
+    const unsigned int tid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+    if (a1 > a0) {
+        const unsigned int sh = (unsigned int)(a0 - p0);             // payload byte that lands on word a0: 0..3
+        const uint32_t *src = (const uint32_t *)payload;
+        uint32_t *dst = (uint32_t *)(out + a0);
+        const unsigned int nw = (unsigned int)((a1 - a0) >> 2);
+        for (unsigned int i = tid; i < nw; i += nthr) {
+            const uint32_t lo = src[i], hi = sh ? src[i + 1] : 0u;  // payload bytes 4i+sh .. 4i+sh+3; i+1 stays inside the
+            dst[i] = __funnelshift_r(lo, hi, 8u * sh);               // 16-byte padded picture because 4i+sh+3 < n
+        }
+    }
+    // the ragged ends: prefix + bytes up to a0, and bytes from a1 to the end of the trailer
+    const unsigned long long e0 = a1 > a0 ? a0 : s1, b1 = a1 > a0 ? a1 : s1;
+    for (unsigned long long g = s0 + tid; g < e0; g += nthr) out[g] = (uint8_t)stream_byte((unsigned int)(g - s0), n, prefix, payload, trailer_be);
+    for (unsigned long long g = b1 + tid; g < s1; g += nthr) out[g] = (uint8_t)stream_byte((unsigned int)(g - s0), n, prefix, payload, trailer_be);
+}
+
 __device__ __forceinline__ uint32_t mix32(uint32_t x)
 {
     x ^= x >> 16; x *= 0x7feb352du; x ^= x >> 15; x *= 0x846ca68bu; x ^= x >> 16;
@@ -754,6 +840,19 @@ cudaError_t m1k_launch_push(uint8_t *dst, const uint8_t *src, const unsigned lon
                             cudaStream_t st)
 {
     k_push_bytes<<<64, 256, 0, st>>>((uint4 *)dst, (const uint4 *)src, end, cap);
+    return cudaGetLastError();
+}
+
+cudaError_t m1k_launch_stream(const uint8_t *payloads, const uint32_t *frame_bytes, const unsigned long long *frame_off,
+                              int n_frames, long first_index, const uint8_t *prefix256, uint32_t trailer_be,
+                              unsigned long long base, unsigned long long *seg_off, uint8_t *out, unsigned long long cap,
+                              int *err, cudaStream_t st)
+{
+    k_stream_offsets<<<1, 1024, 0, st>>>(n_frames, frame_bytes, base, seg_off, cap, err);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dim3 grid(8, n_frames);
+    k_stream_copy<<<grid, 256, 0, st>>>(payloads, frame_bytes, frame_off, seg_off, first_index, prefix256, trailer_be, out, cap);
     return cudaGetLastError();
 }
 

@@ -24,3 +24,7 @@ cudaError_t m1k_launch_synth(uint32_t seed, long first_frame, int n_frames, int 
                              uint8_t *rgb, cudaStream_t st);
 cudaError_t m1k_launch_push(uint8_t *dst, const uint8_t *src, const unsigned long long *end, unsigned long long cap,
                             cudaStream_t st);
+cudaError_t m1k_launch_stream(const uint8_t *payloads, const uint32_t *frame_bytes, const unsigned long long *frame_off,
+                              int n_frames, long first_index, const uint8_t *prefix256, uint32_t trailer_be,
+                              unsigned long long base, unsigned long long *seg_off, uint8_t *out, unsigned long long cap,
+                              int *err, cudaStream_t st);

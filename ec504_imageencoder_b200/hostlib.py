@@ -36,6 +36,7 @@ def lib() -> C.CDLL:
         "mpeg_encode_procedure": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),
         "m1_encode_frames_to_file": (C.c_int, [C.c_char_p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
         "m1_encode_frames_to_memory": (C.c_long, [u8p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_long]),
+        "m1_stream_templates": (None, [C.c_int, C.c_int, C.c_int, u8p, u8p, u8p]),
         "bitvector_new": (bvp, [C.c_char_p, C.c_longlong]),
         "bitvector_put_bit": (None, [bvp, C.c_char]),
         "bitvector_put_binstring": (None, [bvp, C.c_char_p]),
@@ -84,6 +85,14 @@ def encode_frames_to_memory(frames: np.ndarray, quality: int = 12, mode: int = 0
     if got < 0:
         raise RuntimeError(f"m1_encode_frames_to_memory failed ({got})")
     return out[:got].tobytes()
+
+
+def stream_templates(width: int, height: int, mode: int = 0):
+    """(prefix256 [256*44], prologue [27], trailer [4]) as uint8 arrays: the header bytes, written by the host
+    C library's reference-API functions, that M1Encoder.assemble_stream hands to the device."""
+    prefix, prologue, trailer = np.zeros(256 * 44, np.uint8), np.zeros(27, np.uint8), np.zeros(4, np.uint8)
+    lib().m1_stream_templates(int(width), int(height), int(mode), prefix.ctypes.data, prologue.ctypes.data, trailer.ctypes.data)
+    return prefix, prologue, trailer
 
 
 def mpeg_encode_procedure(images_folder: str, bitstream_folder: str, video_path: str, quality_factor: int = 12) -> int:

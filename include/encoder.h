@@ -52,6 +52,14 @@ int m1_encode_frames_to_file(const char *video_path, const unsigned char *frames
 long m1_encode_frames_to_memory(const unsigned char *frames, int n_frames, int width, int height,
                                 int channels, int quality_factor, int mode, unsigned char *out, long cap);
 
+/* The header bytes m1cu_assemble_stream (include/m1cu.h) needs to build the stream image on the device:
+ * prefix256 = 256 x 44 bytes, entry i = the packet / sequence / GOP / picture headers in front of picture
+ * index i (the reference's clock is a uint8_t hour, include/encoder.h:42, so they repeat every 256 pictures;
+ * the packet length is left for an empty payload), prologue = the 27 file bytes of include/encoder.h:86-88,
+ * trailer = the 4 bytes after every picture.  All written by the include/mpeg1_enc.h functions. */
+void m1_stream_templates(int width, int height, int mode, unsigned char prefix256[256 * 44],
+                         unsigned char prologue[27], unsigned char trailer[4]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -160,6 +160,22 @@ int m1cu_ipc_close(int device, void *d_ptr);
 int m1cu_push_payloads(m1cu_ctx *ctx, void *stream, uint8_t *dst, size_t dst_cap, const uint8_t *d_src,
                        const uint64_t *d_frame_offsets, int n_frames);
 
+/* ---- final stream image on the device (optional) --------------------------- */
+/* Turns the result of m1cu_encode_device into the bytes the reference's driver writes to the .mpeg file
+ * (include/encoder.h:196-231, :448-458): [h_prologue, 27 bytes, or NULL] then per picture the 44-byte
+ * prefix, the payload and the 4-byte trailer.  The headers stay the host's business: h_prefix256 holds 256
+ * prefixes of 44 bytes, indexed by (picture index & 255), built with the include/mpeg1_enc.h writers exactly
+ * as for a picture with an empty payload; the device only patches the 16-bit packet length
+ * (44 + payload - 8, unsigned short arithmetic) into bytes 4..5.  Picture f of this call has index
+ * first_frame_index + f.  d_stream (16-byte aligned, stream_cap bytes) receives the image,
+ * *d_stream_bytes its length (device).  Asynchronous on the context's stream; a too small stream_cap is
+ * reported by the next m1cu_check() (M1CU_ERR_CAPACITY).  The host copies of the templates are cached:
+ * they are uploaded again only when their bytes change. */
+int m1cu_assemble_stream(m1cu_ctx *ctx, const uint8_t *d_payloads, const uint32_t *d_frame_bytes,
+                         const uint64_t *d_frame_offsets, int n_frames, long first_frame_index,
+                         const uint8_t *h_prefix256, const uint8_t *h_prologue, const uint8_t h_trailer[4],
+                         uint8_t *d_stream, size_t stream_cap, uint64_t *d_stream_bytes);
+
 #ifdef __cplusplus
 }
 #endif

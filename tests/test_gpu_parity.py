@@ -178,3 +178,33 @@ def test_capacity_error_and_retry(m1, port):
     ok = enc.encode_device(rgb)          # context still usable afterwards
     host = rgb.cpu().numpy()
     assert ok.payloads() == [port.encode_picture(host[f], 50, MODE_FULL) for f in range(2)]
+
+
+@pytest.mark.parametrize("mode,W,H", [(MODE_FULL, 352, 240), (MODE_FULL, 100, 52), (MODE_REF_COMPAT, 400, 600)])
+def test_device_stream_assembly(m1, port, mode, W, H):
+    """m1cu_assemble_stream: the .mpeg bytes built on the device equal the oracle's stream (prologue, 44-byte
+    prefixes with the packet length patched in, payloads, trailers), also for a batch that starts at another
+    picture index and crosses the reference's 256-picture clock wrap, and without the prologue."""
+    import torch
+    n, q = 9, 12
+    enc = m1.M1Encoder(W, H, 3, mode, q, max_frames=n)
+    rgb = enc.synth_rgb(777, 0, n, SYNTH_NATURAL)
+    res = enc.encode_device(rgb)
+    out, nbytes = enc.assemble_stream(res)
+    enc.check()
+    got = out[:int(nbytes.item())].cpu().numpy().tobytes()
+    want = port.encode_stream(rgb.cpu().numpy(), q, mode)
+    assert got == want
+    # same payloads as pictures 250 .. 258 of a longer sequence, appended to an existing file (no prologue)
+    pay = res.payloads()
+    out2, nb2 = enc.assemble_stream(res, first_frame_index=250, prologue=False)
+    enc.check()
+    got2 = out2[:int(nb2.item())].cpu().numpy().tobytes()
+    want2 = b"".join(port.frame_prefix(250 + f, W, H, mode, len(pay[f])) + pay[f] + b"\x00\x00\x01\xb7" for f in range(n))
+    assert got2 == want2
+    # a stream buffer that is too small is reported, not overrun
+    small = torch.zeros(((len(want) // 2) + 15) // 16 * 16, dtype=torch.uint8, device=out.device)
+    enc.assemble_stream(res, out=small)
+    with pytest.raises(m1.M1Error):
+        enc.check()
+    enc.close()

@@ -125,6 +125,19 @@ def test_headers_against_golden(host):
     assert end.tobytes() == b"\x00\x00\x01\xb7"
 
 
+def test_stream_templates_against_oracle(host, port):
+    """m1_stream_templates (the header bytes handed to the device-side stream assembly): every one of the
+    256 prefixes equals the oracle's frame prefix for an empty payload, in both modes; prologue and trailer."""
+    for mode, (W, H) in ((0, (1920, 1080)), (0, (352, 240)), (1, (400, 600))):
+        prefix, prologue, trailer = host.stream_templates(W, H, mode)
+        assert prologue.tobytes() == port.file_prologue()
+        assert trailer.tobytes() == b"\x00\x00\x01\xb7"
+        for i in range(256):
+            assert prefix[44 * i:44 * i + 44].tobytes() == port.frame_prefix(i, W, H, mode, 0), (mode, i)
+        # the reference's clock wraps: picture 256 + i carries the headers of picture i
+        assert port.frame_prefix(256 + 7, W, H, mode, 0) == port.frame_prefix(7, W, H, mode, 0)
+
+
 def test_bitvector_semantics(host):
     L = host.lib()
     bv = L.bitvector_new(b"101", 3)                  # size is a capacity hint, length = strlen
