@@ -103,7 +103,7 @@ def m1cu() -> C.CDLL:
         "m1cu_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
         "m1cu_ipc_close": (C.c_int, [C.c_int, vp]),
         "m1cu_push_payloads": (C.c_int, [vp, vp, u8p, C.c_size_t, u8p, u64p, C.c_int]),
-        "m1cu_assemble_stream": (C.c_int, [vp, u8p, u32p, u64p, C.c_int, C.c_long, vp, vp, vp, u8p, C.c_size_t, u64p]),
+        "m1cu_assemble_stream": (C.c_int, [vp, u8p, u32p, u64p, C.c_int, C.c_long, vp, vp, vp, u8p, C.c_size_t, C.c_size_t, u64p]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name)

@@ -607,7 +607,7 @@ int m1cu_push_payloads(m1cu_ctx *ctx, void *stream, uint8_t *dst, size_t dst_cap
 int m1cu_assemble_stream(m1cu_ctx *ctx, const uint8_t *d_payloads, const uint32_t *d_frame_bytes,
                          const uint64_t *d_frame_offsets, int n_frames, long first_frame_index,
                          const uint8_t *h_prefix256, const uint8_t *h_prologue, const uint8_t h_trailer[4],
-                         uint8_t *d_stream, size_t stream_cap, uint64_t *d_stream_bytes)
+                         uint8_t *d_stream, size_t stream_cap, size_t stream_offset, uint64_t *d_stream_bytes)
 {
     if (!ctx || !d_payloads || !d_frame_bytes || !d_frame_offsets || n_frames <= 0 || !h_prefix256 || !h_trailer ||
         !d_stream || !d_stream_bytes || ((uintptr_t)d_stream & 15) || ((uintptr_t)d_payloads & 15))
@@ -630,11 +630,11 @@ int m1cu_assemble_stream(m1cu_ctx *ctx, const uint8_t *d_payloads, const uint32_
         CU(cudaMalloc(&ctx->d_seg_off, sizeof(unsigned long long) * (size_t)(n_frames + 1)));
         ctx->seg_frames = n_frames + 1;
     }
-    unsigned long long base = 0;
+    unsigned long long base = stream_offset;
     if (h_prologue) {
-        if (stream_cap < 27) return fail(ctx, M1CU_ERR_CAPACITY, "m1cu_assemble_stream: stream_cap too small");
-        CU(cudaMemcpyAsync(d_stream, ctx->d_stream_tmpl + kTmpl, 27, cudaMemcpyDeviceToDevice, st));
-        base = 27;
+        if (stream_cap < stream_offset + 27) return fail(ctx, M1CU_ERR_CAPACITY, "m1cu_assemble_stream: stream_cap too small");
+        CU(cudaMemcpyAsync(d_stream + stream_offset, ctx->d_stream_tmpl + kTmpl, 27, cudaMemcpyDeviceToDevice, st));
+        base += 27;
     }
     const uint32_t trailer_be = ((uint32_t)h_trailer[0] << 24) | ((uint32_t)h_trailer[1] << 16) | ((uint32_t)h_trailer[2] << 8) | h_trailer[3];
     CU(m1k_launch_stream(d_payloads, d_frame_bytes, (const unsigned long long *)d_frame_offsets, n_frames, first_frame_index,

@@ -169,18 +169,19 @@ class M1Encoder:
             self._err(rc)
 
     def assemble_stream(self, res: EncodedBatch, n_frames: int | None = None, first_frame_index: int = 0,
-                        prologue: bool = True, out: torch.Tensor | None = None):
+                        prologue: bool = True, out: torch.Tensor | None = None, offset: int = 0):
         """The bytes of the .mpeg file for a finished encode, assembled on the device (m1cu_assemble_stream):
         [27-byte prologue] + per picture 44-byte prefix, payload, 4-byte trailer.  The header bytes come from the
-        host C library (hostlib.stream_templates).  Returns (uint8 CUDA tensor, its length as a 1-element int64
-        CUDA tensor); asynchronous on the encoder's stream."""
+        host C library (hostlib.stream_templates).  Writing starts at byte `offset` of `out` (continue a stream
+        with the end offset of the previous call).  Returns (uint8 CUDA tensor, the end offset as a 1-element
+        int64 CUDA tensor); asynchronous on the encoder's stream."""
         from . import hostlib
         n = int(res.frame_bytes.numel() if n_frames is None else n_frames)
         if getattr(self, "_tmpl", None) is None:
             self._tmpl = hostlib.stream_templates(self.width, self.height, self.mode)
         prefix, prolog, trailer = self._tmpl
         if out is None:
-            cap = 32 + n * 48 + int(res.out.numel() if res.out_ptr is None else res.out_cap)
+            cap = int(offset) + 32 + n * 48 + int(res.out.numel() if res.out_ptr is None else res.out_cap)
             out = torch.empty((cap + 15) // 16 * 16, dtype=torch.uint8, device=res.frame_bytes.device)
         nbytes = torch.zeros(1, dtype=torch.int64, device=res.frame_bytes.device)
         self._bind_stream()
@@ -188,7 +189,7 @@ class M1Encoder:
         rc = self.lib.m1cu_assemble_stream(self._h, out_ptr, res.frame_bytes.data_ptr(), res.frame_offsets.data_ptr(), n,
                                            int(first_frame_index), prefix.ctypes.data,
                                            prolog.ctypes.data if prologue else None, trailer.ctypes.data,
-                                           out.data_ptr(), out.numel(), nbytes.data_ptr())
+                                           out.data_ptr(), out.numel(), int(offset), nbytes.data_ptr())
         if rc:
             self._err(rc)
         return out, nbytes

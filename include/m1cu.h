@@ -167,14 +167,15 @@ int m1cu_push_payloads(m1cu_ctx *ctx, void *stream, uint8_t *dst, size_t dst_cap
  * prefixes of 44 bytes, indexed by (picture index & 255), built with the include/mpeg1_enc.h writers exactly
  * as for a picture with an empty payload; the device only patches the 16-bit packet length
  * (44 + payload - 8, unsigned short arithmetic) into bytes 4..5.  Picture f of this call has index
- * first_frame_index + f.  d_stream (16-byte aligned, stream_cap bytes) receives the image,
- * *d_stream_bytes its length (device).  Asynchronous on the context's stream; a too small stream_cap is
+ * first_frame_index + f.  d_stream (16-byte aligned, stream_cap bytes) receives the image starting at byte
+ * stream_offset (any value: a later batch, or another rank's pictures, continue where the previous call
+ * ended), *d_stream_bytes (device) the offset one past the last byte written.  Asynchronous on the context's stream; a too small stream_cap is
  * reported by the next m1cu_check() (M1CU_ERR_CAPACITY).  The host copies of the templates are cached:
  * they are uploaded again only when their bytes change. */
 int m1cu_assemble_stream(m1cu_ctx *ctx, const uint8_t *d_payloads, const uint32_t *d_frame_bytes,
                          const uint64_t *d_frame_offsets, int n_frames, long first_frame_index,
                          const uint8_t *h_prefix256, const uint8_t *h_prologue, const uint8_t h_trailer[4],
-                         uint8_t *d_stream, size_t stream_cap, uint64_t *d_stream_bytes);
+                         uint8_t *d_stream, size_t stream_cap, size_t stream_offset, uint64_t *d_stream_bytes);
 
 #ifdef __cplusplus
 }

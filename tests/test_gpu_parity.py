@@ -202,6 +202,14 @@ def test_device_stream_assembly(m1, port, mode, W, H):
     got2 = out2[:int(nb2.item())].cpu().numpy().tobytes()
     want2 = b"".join(port.frame_prefix(250 + f, W, H, mode, len(pay[f])) + pay[f] + b"\x00\x00\x01\xb7" for f in range(n))
     assert got2 == want2
+    # two calls into one buffer: pictures 0..8 with the prologue, then the same payloads again as pictures 9..17
+    end1 = int(nbytes.item())
+    big = torch.zeros((2 * len(want) + 64 + 15) // 16 * 16, dtype=torch.uint8, device=out.device)
+    enc.assemble_stream(res, out=big)
+    _, nb3 = enc.assemble_stream(res, first_frame_index=n, prologue=False, out=big, offset=end1)
+    enc.check()
+    want3 = want + b"".join(port.frame_prefix(n + f, W, H, mode, len(pay[f])) + pay[f] + b"\x00\x00\x01\xb7" for f in range(n))
+    assert int(nb3.item()) == len(want3) and big[:len(want3)].cpu().numpy().tobytes() == want3
     # a stream buffer that is too small is reported, not overrun
     small = torch.zeros(((len(want) // 2) + 15) // 16 * 16, dtype=torch.uint8, device=out.device)
     enc.assemble_stream(res, out=small)
