@@ -38,6 +38,27 @@ class Gathered:
         return out
 
 
+    def assemble_stream(self, enc, first_frame_index: int = 0, prologue: bool = True) -> torch.Tensor:
+        """Rank 0: the ordered .mpeg image of all ranks' pictures, assembled on the device
+        (M1Encoder.assemble_stream / m1cu_assemble_stream, one call per rank's segment, each continuing
+        where the previous one ended).  Returns the uint8 CUDA tensor holding exactly the stream bytes."""
+        from .encoder import EncodedBatch
+        counts = [int(s.numel()) for s in self.sizes]
+        ends = [int(o[-1].item()) if c else 0 for o, c in zip(self.offsets, counts)]     # one small sync per rank
+        cap = 32 + sum(48 * c + e for c, e in zip(counts, ends))
+        out = torch.empty((cap + 15) // 16 * 16, dtype=torch.uint8, device=self.segments[0].device)
+        off, index, first = 0, int(first_frame_index), True
+        for s, o, seg, c in zip(self.sizes, self.offsets, self.segments, counts):
+            if c == 0:
+                continue
+            b = EncodedBatch(out=seg, frame_bytes=s.contiguous(), frame_offsets=o.contiguous(), levels=None)
+            _, end = enc.assemble_stream(b, n_frames=c, first_frame_index=index, prologue=prologue and first,
+                                         out=out, offset=off)
+            off, index, first = int(end.item()), index + c, False
+        enc.check()
+        return out[:off]
+
+
 def gather_to_rank0(out: torch.Tensor, frame_bytes: torch.Tensor, frame_offsets: torch.Tensor,
                     frames_per_rank: list[int], recv: torch.Tensor | None = None, group=None) -> Gathered | None:
     """Collective.  `out`/`frame_bytes`/`frame_offsets` are this rank's EncodedBatch fields;

@@ -22,7 +22,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 from ec504_imageencoder_b200 import M1Encoder, MODE_FULL, SYNTH_NATURAL, hostlib  # noqa: E402
-from ec504_imageencoder_b200.distributed import PeerGather, frame_range, gather_to_rank0  # noqa: E402
+from ec504_imageencoder_b200.distributed import Gathered, PeerGather, frame_range, gather_to_rank0  # noqa: E402
 
 
 def frame_prefix(L, index, W, H, payload_bytes):
@@ -50,6 +50,8 @@ def main():
     ap.add_argument("--verify", action="store_true")
     ap.add_argument("--peer", action="store_true", help="payloads go to rank 0 through NVLink peer memory (PeerGather)")
     ap.add_argument("--staged", action="store_true", help="with --peer: local stitch + push kernel instead of a remote stitch")
+    ap.add_argument("--device-stream", action="store_true",
+                    help="rank 0 assembles the final file image on its GPU (m1cu_assemble_stream) instead of on the host")
     a = ap.parse_args()
 
     rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
@@ -68,16 +70,23 @@ def main():
         if hi > lo:
             enc.encode_device(rgb.contiguous(), res=res)
         g = pg.finish(0, counts)
-        payloads = g.payloads() if rank == 0 else None
     elif world > 1:
         res = enc.encode_device(rgb.contiguous()) if hi > lo else enc.alloc_outputs(1)
         g = gather_to_rank0(res.out, res.frame_bytes, res.frame_offsets, counts)
-        payloads = g.payloads() if rank == 0 else None
     else:
-        payloads = enc.encode_device(rgb.contiguous()).payloads()
+        res = enc.encode_device(rgb.contiguous())
+        g = Gathered(sizes=[res.frame_bytes], offsets=[res.frame_offsets], segments=[res.out])
+    image = payloads = None
+    if rank == 0 and a.device_stream:
+        image = g.assemble_stream(enc).cpu().numpy().tobytes()      # headers from libencoder, bytes placed by the GPU
+    elif rank == 0:
+        payloads = g.payloads()
 
     ok = True
-    if rank == 0:
+    if rank == 0 and image is not None:
+        with open(a.out, "wb") as f:
+            f.write(image)
+    elif rank == 0:
         L = hostlib.lib()
         pro = np.zeros(27, np.uint8)
         L.mpeg1_file_header(2202035, pro.ctypes.data)
@@ -88,6 +97,7 @@ def main():
                 f.write(frame_prefix(L, i, a.width, a.height, len(p)))
                 f.write(p)
                 f.write(b"\x00\x00\x01\xb7")
+    if rank == 0:
         size = os.path.getsize(a.out)
         print(f"rank 0: {a.frames} frames from {world} GPU(s) -> {a.out} ({size} bytes)")
         if a.verify:

@@ -44,15 +44,19 @@ def test_kernel_variant(env):
     assert out.returncode == 0 and "VARIANT_OK" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
 
 
-def test_sharded_example_matches_oracle(tmp_path):
-    """examples/encode_sharded.py: frame-range sharding + NCCL gather to rank 0 + host headers gives the
-    oracle's byte stream.  Runs with 2 ranks when the box has 2 GPUs, else with 1."""
+@pytest.mark.parametrize("device_stream", [False, True])
+def test_sharded_example_matches_oracle(tmp_path, device_stream):
+    """examples/encode_sharded.py: frame-range sharding + NCCL gather to rank 0 + host headers (or, with
+    --device-stream, the file image assembled on rank 0's GPU) gives the oracle's byte stream.  Runs with 2
+    ranks when the box has 2 GPUs, else with 1."""
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
     n = 2 if torch.cuda.device_count() >= 2 else 1
     out = str(tmp_path / "s.mpeg")
     script = os.path.join(ROOT, "examples", "encode_sharded.py")
     args = ["--frames", "7", "--width", "352", "--height", "240", "--out", out, "--verify"]
+    if device_stream:
+        args.append("--device-stream")
     if n == 1:
         cmd = [sys.executable, script] + args
     else:
