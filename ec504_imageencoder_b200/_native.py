@@ -103,6 +103,7 @@ def m1cu() -> C.CDLL:
         "m1cu_ipc_open": (C.c_int, [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]),
         "m1cu_ipc_close": (C.c_int, [C.c_int, vp]),
         "m1cu_push_payloads": (C.c_int, [vp, vp, u8p, C.c_size_t, u8p, u64p, C.c_int]),
+        "m1cu_encode_host_stream": (C.c_int, [vp, u8p, C.c_int, C.c_long, vp, vp, vp, u8p, C.c_size_t, C.POINTER(C.c_size_t)]),
         "m1cu_assemble_stream": (C.c_int, [vp, u8p, u32p, u64p, C.c_int, C.c_long, vp, vp, vp, u8p, C.c_size_t, C.c_size_t, u64p]),
     }
     for name, (res, args) in sig.items():
@@ -122,4 +123,5 @@ M1CU_SYMBOLS = (
     "m1cu_device_alloc", "m1cu_device_free", "m1cu_pinned_alloc", "m1cu_pinned_free",
     "m1cu_memcpy_h2d", "m1cu_memcpy_d2h",
     "m1cu_ipc_export", "m1cu_ipc_open", "m1cu_ipc_close", "m1cu_push_payloads", "m1cu_assemble_stream",
+    "m1cu_encode_host_stream",
 )

@@ -100,6 +100,19 @@ static int encode_batch(m1cu_ctx *ctx, const unsigned char *batch, int n, long f
                         int mode, unsigned char *payloads, size_t payload_cap, uint32_t *sizes,
                         sink_fn sink, void *cookie)
 {
+    if (env_int("M1_DEVICE_STREAM", 0)) {
+        /* the GPU also places the header, payload and trailer bytes: one download, one write per batch */
+        static unsigned char prefix256[256 * 44];
+        unsigned char prologue[27], trailer[4];
+        size_t bytes = 0;
+        m1_stream_templates(width, height, mode, prefix256, prologue, trailer);
+        const int src = m1cu_encode_host_stream(ctx, batch, n, first, prefix256, NULL, trailer, payloads, payload_cap, &bytes);
+        if (src != M1CU_OK) {
+            printf("Error: GPU encode failed (%d): %s\n", src, m1cu_last_error(ctx));
+            return src;
+        }
+        return sink(cookie, payloads, bytes) ? M1CU_ERR_CAPACITY : M1CU_OK;
+    }
     size_t total = 0;
     const int rc = m1cu_encode_host(ctx, batch, n, payloads, payload_cap, sizes, NULL, &total);
     if (rc != M1CU_OK) {
@@ -128,7 +141,7 @@ static int encode_frames(const unsigned char *frames, int n_frames, int width, i
     const int batch = n_frames < M1_BATCH ? n_frames : M1_BATCH;
     int rc = m1cu_create(&ctx, env_int("M1_DEVICE", 0), width, height, channels, mode, quality, batch);
     if (rc != M1CU_OK) { printf("Error: cannot create the GPU encoder (%d): %s\n", rc, m1cu_last_error(NULL)); return rc; }
-    const size_t cap = m1cu_payload_bound(ctx) * (size_t)batch;
+    const size_t cap = (m1cu_payload_bound(ctx) + 48) * (size_t)batch;   /* + headers and trailer when the GPU assembles the stream */
     unsigned char *payloads = (unsigned char *)malloc(cap);
     uint32_t *sizes = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)batch);
     uint8_t prologue[27];
@@ -241,7 +254,7 @@ int mpeg_encode_procedure(const char *images_folder, const char *bitstream_folde
             printf("Error: cannot create the GPU encoder (%d): %s\n", rc, m1cu_last_error(NULL));
             rc = -1;
         } else {
-            const size_t cap = m1cu_payload_bound(ctx) * (size_t)batch;
+            const size_t cap = (m1cu_payload_bound(ctx) + 48) * (size_t)batch;   /* + headers and trailer when the GPU assembles the stream */
             unsigned char *staging = (unsigned char *)m1cu_pinned_alloc(fsz * (size_t)batch);
             unsigned char *payloads = (unsigned char *)malloc(cap);
             uint32_t *sizes = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)batch);

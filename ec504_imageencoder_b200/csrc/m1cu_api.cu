@@ -43,6 +43,8 @@ struct m1cu_ctx {
     // m1cu_assemble_stream: prefix templates (256 x 44) + prologue (27) on the device, the host copy they came from
     uint8_t *d_stream_tmpl = nullptr;
     unsigned long long *d_seg_off = nullptr; int seg_frames = 0;
+    uint8_t *d_stream = nullptr; size_t d_stream_cap = 0;     // m1cu_encode_host_stream
+    unsigned long long *d_stream_end = nullptr;
     std::vector<uint8_t> h_stream_tmpl;
     int *d_err = nullptr;
     unsigned long long *d_running = nullptr;
@@ -239,7 +241,7 @@ int m1cu_destroy(m1cu_ctx *ctx)
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->d_staging); cudaFree(ctx->d_chunk_bits); cudaFree(ctx->d_chunk_dst);
-    cudaFree(ctx->d_tables); cudaFree(ctx->d_stream_tmpl); cudaFree(ctx->d_seg_off); cudaFree(ctx->d_err); cudaFree(ctx->d_running); cudaFree(ctx->d_done);
+    cudaFree(ctx->d_tables); cudaFree(ctx->d_stream_tmpl); cudaFree(ctx->d_seg_off); cudaFree(ctx->d_stream); cudaFree(ctx->d_stream_end); cudaFree(ctx->d_err); cudaFree(ctx->d_running); cudaFree(ctx->d_done);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_fbytes); cudaFree(ctx->d_foff);
     cudaFree(ctx->d_levels);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
@@ -642,6 +644,55 @@ int m1cu_assemble_stream(m1cu_ctx *ctx, const uint8_t *d_payloads, const uint32_
                          ctx->d_err, st));
     CU(cudaMemcpyAsync(d_stream_bytes, ctx->d_seg_off + n_frames, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
     ctx->launches += 2;
+    return M1CU_OK;
+}
+
+int m1cu_encode_host_stream(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, long first_frame_index,
+                            const uint8_t *h_prefix256, const uint8_t *h_prologue, const uint8_t h_trailer[4],
+                            uint8_t *h_stream, size_t stream_cap, size_t *stream_bytes)
+{
+    if (!ctx || !h_rgb || !h_stream || !stream_bytes || n_frames <= 0 || !h_prefix256 || !h_trailer)
+        return fail(ctx, M1CU_ERR_ARG, "m1cu_encode_host_stream: bad argument");
+    if (n_frames > ctx->max_frames) return fail(ctx, M1CU_ERR_ARG, "m1cu_encode_host_stream: n_frames > max_frames");
+    const M1Geom &g = ctx->g;
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const size_t in_bytes = (size_t)g.frame_stride * n_frames;
+    int rc;
+    if ((rc = ensure(ctx, (void **)&ctx->d_in, &ctx->d_in_cap, in_bytes))) return rc;
+    if (ctx->d_meta_frames < n_frames) {
+        cudaFree(ctx->d_fbytes); cudaFree(ctx->d_foff); ctx->d_fbytes = nullptr; ctx->d_foff = nullptr;
+        if (ctx->h_fbytes) cudaFreeHost(ctx->h_fbytes);
+        if (ctx->h_foff) cudaFreeHost(ctx->h_foff);
+        ctx->h_fbytes = nullptr; ctx->h_foff = nullptr; ctx->d_meta_frames = 0;
+        CU(cudaMalloc(&ctx->d_fbytes, sizeof(uint32_t) * n_frames));
+        CU(cudaMalloc(&ctx->d_foff, sizeof(unsigned long long) * (n_frames + 1)));
+        CU(cudaMallocHost(&ctx->h_fbytes, sizeof(uint32_t) * n_frames));
+        CU(cudaMallocHost(&ctx->h_foff, sizeof(unsigned long long) * (n_frames + 1)));
+        ctx->d_meta_frames = n_frames;
+    }
+    if (!ctx->d_stream_end) CU(cudaMalloc(&ctx->d_stream_end, sizeof(unsigned long long)));
+    CU(cudaMemcpyAsync(ctx->d_in, h_rgb, in_bytes, cudaMemcpyHostToDevice, st));
+    size_t want = m1cu_typical_out_bytes(ctx, n_frames);
+    unsigned long long end = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        if ((rc = ensure(ctx, (void **)&ctx->d_out, &ctx->d_out_cap, want))) return rc;
+        if ((rc = ensure(ctx, (void **)&ctx->d_stream, &ctx->d_stream_cap, want + 48 * (size_t)n_frames + 32))) return rc;
+        if ((rc = m1cu_encode_device(ctx, ctx->d_in, n_frames, ctx->d_out, ctx->d_out_cap, ctx->d_fbytes,
+                                     (uint64_t *)ctx->d_foff, nullptr))) return rc;
+        if ((rc = m1cu_assemble_stream(ctx, ctx->d_out, ctx->d_fbytes, (const uint64_t *)ctx->d_foff, n_frames, first_frame_index,
+                                       h_prefix256, h_prologue, h_trailer, ctx->d_stream, ctx->d_stream_cap, 0,
+                                       (uint64_t *)ctx->d_stream_end))) return rc;
+        CU(cudaMemcpyAsync(&end, ctx->d_stream_end, sizeof end, cudaMemcpyDeviceToHost, st));
+        rc = m1cu_check(ctx);                                        // synchronises
+        if (rc == M1CU_ERR_CAPACITY && attempt == 0) { want = m1cu_payload_bound(ctx) * (size_t)n_frames; continue; }
+        if (rc) return rc;
+        break;
+    }
+    if (end > stream_cap) return fail(ctx, M1CU_ERR_CAPACITY, "m1cu_encode_host_stream: h_stream too small");
+    CU(cudaMemcpyAsync(h_stream, ctx->d_stream, (size_t)end, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    *stream_bytes = (size_t)end;
     return M1CU_OK;
 }
 

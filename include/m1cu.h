@@ -177,6 +177,13 @@ int m1cu_assemble_stream(m1cu_ctx *ctx, const uint8_t *d_payloads, const uint32_
                          const uint8_t *h_prefix256, const uint8_t *h_prologue, const uint8_t h_trailer[4],
                          uint8_t *d_stream, size_t stream_cap, size_t stream_offset, uint64_t *d_stream_bytes);
 
+/* Host-buffer form of the two calls above: upload, encode, assemble on the device, ONE download of the
+ * finished bytes into h_stream (capacity stream_cap); *stream_bytes = their count.  Synchronous.  What
+ * mpeg_encode_procedure uses when M1_DEVICE_STREAM=1. */
+int m1cu_encode_host_stream(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, long first_frame_index,
+                            const uint8_t *h_prefix256, const uint8_t *h_prologue, const uint8_t h_trailer[4],
+                            uint8_t *h_stream, size_t stream_cap, size_t *stream_bytes);
+
 #ifdef __cplusplus
 }
 #endif
