@@ -216,3 +216,26 @@ def test_device_stream_assembly(m1, port, mode, W, H):
     with pytest.raises(m1.M1Error):
         enc.check()
     enc.close()
+
+
+def test_host_stream_entry_point(m1, port):
+    """m1cu_encode_host_stream through the C ABI: host pictures in, finished file bytes out (equal to the
+    oracle's stream); a too small host buffer is an error, not an overrun."""
+    import ctypes as C
+    from ec504_imageencoder_b200 import _native, hostlib
+    W, H, n, q = 176, 144, 6, 12
+    frames = np.stack([port.synth_rgb(5, f, W, H, SYNTH_NOISE) for f in range(n)])
+    want = port.encode_stream(frames, q, MODE_FULL)
+    prefix, prologue, trailer = hostlib.stream_templates(W, H, MODE_FULL)
+    enc = m1.M1Encoder(W, H, 3, MODE_FULL, q, max_frames=n)
+    lib = _native.m1cu()
+    out = np.zeros(len(want) + 64, np.uint8)
+    got = C.c_size_t(0)
+    rc = lib.m1cu_encode_host_stream(enc._h, frames.ctypes.data, n, 0, prefix.ctypes.data, prologue.ctypes.data,
+                                     trailer.ctypes.data, out.ctypes.data, out.size, C.byref(got))
+    assert rc == 0 and out[:got.value].tobytes() == want
+    small = np.zeros(len(want) // 2, np.uint8)
+    rc = lib.m1cu_encode_host_stream(enc._h, frames.ctypes.data, n, 0, prefix.ctypes.data, prologue.ctypes.data,
+                                     trailer.ctypes.data, small.ctypes.data, small.size, C.byref(got))
+    assert rc == -3
+    enc.close()
