@@ -205,3 +205,29 @@ def test_coder_flags_unencodable_level(bh, port):
     # ... but not when the coefficient sits behind the stop point and is never coded
     assert code_levels(bh, _zz([(0, 3), (1, 1), (5, 300)]), True)[1] == 0
 
+
+
+def test_block_functions_property(bh, port):
+    """Property test (hypothesis): any 8x8 block of bytes, any quality the reference can encode (<= 89, SURVEY.md
+    section 7), luma or chroma, any record slot and swizzle key -> DCT, levels, mask, bits and register
+    accumulator equal the oracle's."""
+    hyp = pytest.importorskip("hypothesis")
+    st = pytest.importorskip("hypothesis.strategies")
+
+    @hyp.settings(max_examples=400, deadline=None, derandomize=True)
+    @hyp.given(st.binary(min_size=64, max_size=64), st.integers(1, 89), st.booleans(), st.booleans(),
+               st.integers(0, 95), st.integers(0, 7))
+    def check(raw, quality, is_luma, first, tid, key):
+        blk = np.frombuffer(raw, np.uint8)
+        qm = port.qmatrix(quality)
+        assert bh.m1bh_set_matrix(qm.ctypes.data) == 0
+        dct, lev, bits, (hi, lo, n), nz, bad = run_block(bh, blk, is_luma, first, tid, key)
+        ref_dct = port.fdct8x8(blk)
+        ref_zz = port.quant_zigzag(ref_dct, qm)
+        assert np.array_equal(dct, ref_dct) and np.array_equal(lev.astype(np.int32), ref_zz)
+        want = ("11" if first else "") + port.block_bits(ref_zz, is_luma)
+        assert bits == want and n == len(want) and bad == 0
+        if n <= 64:
+            assert f"{(hi << 32) | lo:064b}"[:n] == want
+
+    check()
