@@ -42,7 +42,7 @@ def _nvcc() -> str:
 def build_cuda(force: bool = False, verbose: bool = False) -> str:
     srcs = [os.path.join(CSRC, s) for s in CUDA_SOURCES]
     deps = srcs + [os.path.join(CSRC, h) for h in ("m1cu_common.cuh", "m1cu_kernels.h", "m1cu_tables.h", "m1cu_block.cuh",
-                                                   "m1cu_quant.h", "m1cu_encode_ws.cuh", "m1cu_encode_persist.cuh")]
+                                                   "m1cu_quant.h", "m1cu_colour.cuh")]
     deps.append(os.path.join(ROOT, "include", "m1cu.h"))
     if not force and _newer(LIB_M1CU, deps):
         return LIB_M1CU
@@ -78,6 +78,7 @@ def m1cu() -> C.CDLL:
         "m1cu_qmatrix": (C.c_int, [C.c_int, i32p]),
         "m1cu_last_error": (C.c_char_p, [vp]),
         "m1cu_create": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+        "m1cu_create_ex": (C.c_int, [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp]),
         "m1cu_destroy": (C.c_int, [vp]),
         "m1cu_set_stream": (C.c_int, [vp, vp]),
         "m1cu_synchronize": (C.c_int, [vp]),
@@ -115,7 +116,7 @@ def m1cu() -> C.CDLL:
 
 
 M1CU_SYMBOLS = (
-    "m1cu_abi_version", "m1cu_device_count", "m1cu_qmatrix", "m1cu_last_error", "m1cu_create",
+    "m1cu_abi_version", "m1cu_device_count", "m1cu_qmatrix", "m1cu_last_error", "m1cu_create", "m1cu_create_ex",
     "m1cu_destroy", "m1cu_set_stream", "m1cu_synchronize", "m1cu_macroblocks_per_frame",
     "m1cu_frame_bytes_in", "m1cu_payload_bound", "m1cu_typical_out_bytes", "m1cu_encode_device",
     "m1cu_check", "m1cu_encode_host", "m1cu_ycbcr_planes", "m1cu_synth_rgb", "m1cu_launch_count",

@@ -6,6 +6,10 @@
 #include "m1cu_kernels.h"
 #include "m1cu_quant.h"
 
+#ifdef M1_EXPERIMENTS
+#include "../../tools/experiments/m1x_env.h"
+#endif
+
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -148,6 +152,12 @@ int m1cu_qmatrix(int quality, int32_t out[64])
 int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels, int mode,
                 int quality, int max_frames)
 {
+    return m1cu_create_ex(out, device, width, height, channels, mode, quality, max_frames, nullptr);
+}
+
+int m1cu_create_ex(m1cu_ctx **out, int device, int width, int height, int channels, int mode,
+                   int quality, int max_frames, const m1cu_tuning *tuning)
+{
     m1cu_ctx *ctx = nullptr;
     if (!out) return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: out is NULL");
     *out = nullptr;
@@ -171,15 +181,18 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     if (mode == M1CU_MODE_FULL) { g.slices = (height + 15) / 16; g.mbs_per_slice = (width + 15) / 16; }
     else                        { g.slices = 6; g.mbs_per_slice = 9; }
     int max_chunk = M1_DEFAULT_CHUNK_MBS;
-    if (const char *v = getenv("M1_CHUNK_MBS")) {          // tuning knob (1..M1_MAX_CHUNK_MBS)
-        const int c = atoi(v);
-        if (c >= 1 && c <= M1_MAX_CHUNK_MBS) max_chunk = c;
+    if (tuning && tuning->chunk_mbs) {
+        if (tuning->chunk_mbs < 1 || tuning->chunk_mbs > M1_MAX_CHUNK_MBS) {
+            delete ctx;
+            return fail(nullptr, M1CU_ERR_ARG, "m1cu_create_ex: chunk_mbs out of range");
+        }
+        max_chunk = tuning->chunk_mbs;
     }
     // Full chunks plus one shorter tail per slice (1080p: 7 x 16 + 8 macroblocks): a full chunk fills its
     // three block warps and four colour warps completely, which beats equal chunks of 15 by 1.7 %.
-    // M1_CHUNK_EVEN=1 restores the equal split.
+    // tuning->chunk_even restores the equal split.
     g.chunk_mbs = max_chunk < g.mbs_per_slice ? max_chunk : g.mbs_per_slice;
-    if (getenv("M1_CHUNK_EVEN") && atoi(getenv("M1_CHUNK_EVEN")) == 1) {
+    if (tuning && tuning->chunk_even) {
         g.chunks_per_slice = (g.mbs_per_slice + max_chunk - 1) / max_chunk;
         g.chunk_mbs = (g.mbs_per_slice + g.chunks_per_slice - 1) / g.chunks_per_slice;
     }
@@ -195,11 +208,18 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     g.frame_stride = (unsigned long long)width * height * channels;
     // 128-bit tile loads need 16-pixel tiles to start on 16-byte boundaries in every row and picture
     g.fast_load = (mode == M1CU_MODE_FULL && (channels == 3 || channels == 4) && width % 16 == 0) ? channels : 0;
-    g.debug_skip = getenv("M1_DEBUG_SKIP") ? atoi(getenv("M1_DEBUG_SKIP")) : 0;
+#ifdef M1_EXPERIMENTS
+    g.debug_skip = m1x_env_int("M1_DEBUG_SKIP");           // tools/ profiling build only
+#else
+    g.debug_skip = 0;
+#endif
     g.win_words = M1_WIN_WORDS;
-    if (const char *v = getenv("M1_WIN_WORDS")) {          // test knob: force the multi-window path
-        const int w = atoi(v);
-        if (w >= 4 && w <= M1_WIN_WORDS) g.win_words = w;
+    if (tuning && tuning->win_words) {                     // tests: force the multi-window path
+        if (tuning->win_words < 4 || tuning->win_words > M1_WIN_WORDS) {
+            delete ctx;
+            return fail(nullptr, M1CU_ERR_ARG, "m1cu_create_ex: win_words out of range");
+        }
+        g.win_words = tuning->win_words;
     }
 
     m1cu_qmatrix(quality, ctx->qm);
@@ -215,6 +235,7 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     size_t batch = ((size_t)2 << 30) / per_frame;
     if (batch < 1) batch = 1;
     if (batch > (size_t)max_frames) batch = (size_t)max_frames;
+    if (batch > 65535) batch = 65535;                       // grid.z of k_encode_chunks / grid.y of k_stitch
     ctx->batch_frames = (int)batch;
     CUC(cudaMalloc(&ctx->d_staging, per_frame * batch));
     CUC(cudaMalloc(&ctx->d_chunk_bits, sizeof(uint32_t) * g.chunks_per_frame * batch));
@@ -223,12 +244,15 @@ int m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
     CUC(cudaMalloc(&ctx->d_err, sizeof(int)));
     CUC(cudaMalloc(&ctx->d_running, sizeof(unsigned long long)));
     CUC(cudaMalloc(&ctx->d_done, sizeof(unsigned int)));
-    CUC(cudaMemset(ctx->d_err, 0, sizeof(int)));
-    CUC(cudaMemset(ctx->d_done, 0, sizeof(unsigned int)));
-    CUC(cudaMemset(ctx->d_running, 0, sizeof(unsigned long long)));
+    // Everything below is ordered on the context's own (non-blocking) stream and waited for here: the
+    // legacy default stream does not order against it.
+    CUC(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+    CUC(cudaMemsetAsync(ctx->d_done, 0, sizeof(unsigned int), ctx->stream));
+    CUC(cudaMemsetAsync(ctx->d_running, 0, sizeof(unsigned long long), ctx->stream));
     M1Tables ht;
     m1k_fill_tables(&ht, ctx->q);
-    CUC(cudaMemcpy(ctx->d_tables, &ht, sizeof ht, cudaMemcpyHostToDevice));
+    CUC(cudaMemcpyAsync(ctx->d_tables, &ht, sizeof ht, cudaMemcpyHostToDevice, ctx->stream));
+    CUC(cudaStreamSynchronize(ctx->stream));                // `ht` is a stack object
     CUC(m1k_prepare(g));
 #undef CUC
     *out = ctx;
@@ -342,9 +366,12 @@ int m1cu_check(m1cu_ctx *ctx)
 {
     if (!ctx) return M1CU_ERR_ARG;
     int flags = 0;
+    CU(cudaMemcpyAsync(&flags, ctx->d_err, sizeof flags, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaMemcpy(&flags, ctx->d_err, sizeof flags, cudaMemcpyDeviceToHost));
-    if (flags) CU(cudaMemset(ctx->d_err, 0, sizeof(int)));
+    if (flags) {
+        CU(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     if (flags & M1_ERRBIT_CAPACITY) return fail(ctx, M1CU_ERR_CAPACITY, "output buffer too small for the encoded payloads");
     if (flags & M1_ERRBIT_LEVEL) return fail(ctx, M1CU_ERR_LEVEL, "coded AC level with |L| >= 256 (outside the reference's encodable range)");
     return M1CU_OK;
@@ -560,7 +587,13 @@ void *m1cu_device_alloc(size_t bytes) { void *p = nullptr; if (cudaMalloc(&p, by
 void  m1cu_device_free(void *p) { if (p) cudaFree(p); }
 void *m1cu_pinned_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 void  m1cu_pinned_free(void *p) { if (p) cudaFreeHost(p); }
-int   m1cu_memcpy_h2d(void *dst, const void *src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? M1CU_OK : M1CU_ERR_CUDA; }
+// A pageable source is only staged when cudaMemcpy returns; the wait on the legacy stream makes the
+// bytes visible to work submitted afterwards on the contexts' non-blocking streams.
+int   m1cu_memcpy_h2d(void *dst, const void *src, size_t bytes)
+{
+    if (cudaMemcpy(dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return M1CU_ERR_CUDA;
+    return cudaStreamSynchronize(cudaStreamLegacy) == cudaSuccess ? M1CU_OK : M1CU_ERR_CUDA;
+}
 int   m1cu_memcpy_d2h(void *dst, const void *src, size_t bytes) { return cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? M1CU_OK : M1CU_ERR_CUDA; }
 
 int m1cu_ipc_export(void *d_ptr, unsigned char handle[M1CU_IPC_HANDLE_BYTES])
@@ -623,7 +656,8 @@ int m1cu_assemble_stream(m1cu_ctx *ctx, const uint8_t *d_payloads, const uint32_
     if (h_prologue) memcpy(want.data() + kTmpl, h_prologue, 27);
     if (want != ctx->h_stream_tmpl) {                                // first call, or the caller changed the headers
         CU(cudaStreamSynchronize(st));                               // nobody reads the old templates any more
-        CU(cudaMemcpy(ctx->d_stream_tmpl, want.data(), kAll, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(ctx->d_stream_tmpl, want.data(), kAll, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));                               // pageable source: landed before `want` goes away
         ctx->h_stream_tmpl.swap(want);
     }
     if (ctx->seg_frames < n_frames + 1) {

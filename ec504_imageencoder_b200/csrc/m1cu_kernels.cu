@@ -3,68 +3,11 @@
 #include "m1cu_common.cuh"
 #include "m1cu_kernels.h"
 #include "m1cu_block.cuh"
+#include "m1cu_colour.cuh"
 #include "m1cu_quant.h"
-
-// -------------------------------------------------------------------------------------------
-// Exact colour conversion.  The reference (source/image_processing.c:104-106) evaluates
-//   Y  = (uchar)(0.299 r + 0.587 g + 0.114 b)
-//   Cb = (uchar)(128 - 0.168736 r - 0.331264 g + 0.5 b)
-//   Cr = (uchar)(128 + 0.5 r - 0.418688 g - 0.081312 b)
-// in IEEE double, left to right, products rounded separately (gcc -O0, SSE2, no FMA), then
-// truncates.  __dmul_rn/__dadd_rn/__dsub_rn are never contracted into FMAs, so this is the same
-// arithmetic bit for bit.
-// -------------------------------------------------------------------------------------------
-// int -> double and double -> int go through the 2^52 mantissa trick instead of I2F/F2I (those run
-// on the 16-lane/SM XU pipe): 2^52 + v holds v in its low word, and adding 2^52 with round-toward-
-// zero leaves trunc(x) there (x >= 0 always holds here: Y >= 0, Cb, Cr >= 0.5).  0.5*x is exact, so
-// fma(0.5, x, acc) rounds once exactly like the reference's separate multiply and add.
-__device__ __forceinline__ double u8_to_double(int v)
-{
-    return __dsub_rn(__hiloint2double(0x43300000, v), 4503599627370496.0);
-}
-__device__ __forceinline__ int trunc_nonneg(double x)
-{
-    return __double2loint(__dadd_rz(x, 4503599627370496.0));
-}
-__device__ __forceinline__ void ycbcr_from_doubles(double rd, double gd, double bd, int &y, int &cb, int &cr);
-__device__ __forceinline__ void ycbcr_exact(int r, int g, int b, int &y, int &cb, int &cr)
-{
-    ycbcr_from_doubles(u8_to_double(r), u8_to_double(g), u8_to_double(b), y, cb, cr);
-}
-// byte B of w as a double: one I2F.F64.U8 with a byte selector (XU pipe), no extraction ALU op
-__device__ __forceinline__ double byte_to_double(uint32_t w, int b)   // b is a constant after unrolling
-{
-    double d;
-    const uint32_t s = w >> (8 * b);
-    asm("cvt.rn.f64.u8 %0, %1;" : "=d"(d) : "r"(s));
-    return d;
-}
-// The seven non-trivial coefficients live in constant memory so the FP64 instructions take them as
-// constant-bank operands instead of re-materialising 64-bit immediates through uniform registers.
-__constant__ double kYcc[7] = { 0.299, 0.587, 0.114, 0.168736, 0.331264, 0.418688, 0.081312 };
-
-__device__ __forceinline__ int luma_from_doubles(double rd, double gd, double bd)
-{
-    double t = __dadd_rn(__dmul_rn(kYcc[0], rd), __dmul_rn(kYcc[1], gd));
-    t = __dadd_rn(t, __dmul_rn(kYcc[2], bd));
-    return trunc_nonneg(t);
-}
-__device__ __forceinline__ void chroma_from_doubles(double rd, double gd, double bd, int &cb, int &cr)
-{
-    double u = __dsub_rn(128.0, __dmul_rn(kYcc[3], rd));
-    u = __dsub_rn(u, __dmul_rn(kYcc[4], gd));
-    u = __fma_rn(0.5, bd, u);
-    cb = trunc_nonneg(u);
-    double v = __fma_rn(0.5, rd, 128.0);
-    v = __dsub_rn(v, __dmul_rn(kYcc[5], gd));
-    v = __dsub_rn(v, __dmul_rn(kYcc[6], bd));
-    cr = trunc_nonneg(v);
-}
-__device__ __forceinline__ void ycbcr_from_doubles(double rd, double gd, double bd, int &y, int &cb, int &cr)
-{
-    y = luma_from_doubles(rd, gd, bd);
-    chroma_from_doubles(rd, gd, bd, cb, cr);
-}
+#ifdef M1_EXPERIMENTS
+#include "../../tools/experiments/m1x_env.h"
+#endif
 
 // -------------------------------------------------------------------------------------------
 // Shared-memory plane layout.  Samples are int32, block-major: block `blk` owns 64 words; its
@@ -131,14 +74,15 @@ __device__ __forceinline__ const uint8_t *px_ptr(const uint8_t *frame, const M1G
     return frame + ((size_t)y * g.W + x) * g.channels;
 }
 
-// byte j (0..16*CH-1) of a 16-pixel row held in w[]
-#define M1_ROW_BYTE_D(w, j) byte_to_double((w)[(j) >> 2], (j) & 3)
-
 // Fast half-tile: 8 pixels x 2 rows = the 2x8 strip of luma block column `bc` of the chunk in rows
 // 2*qy, 2*qy+1 of the macroblock row, plus the four 2x2 chroma means under it; everything in range
-// and aligned.  64/128-bit loads, one I2F.F64.U8 per byte (byte selector, no extraction ALU op),
-// 18 FP64 ops per pixel, 128-bit swizzled stores of int32 samples.  Called from a runtime loop so
-// the body exists once in the instruction stream.
+// and aligned.  64/128-bit loads, then the integer colour path of m1cu_colour.cuh straight from the
+// packed bytes: per pixel six IDP.2A (numerators), three IMAD.WIDE (quotient in the high word, scaled
+// fraction in the low word) and the running minimum of the low words of its 2x2 quad.  128-bit
+// swizzled stores of int32 samples.  Returns the four quad minima folded into one flag word: bit q
+// set <=> quad q (pixels 2q, 2q+1 of both rows) holds a pixel whose quotient the integer path cannot
+// vouch for; the caller queues those quads for the exact (double) recomputation.
+// Called from a runtime loop so the body exists once in the instruction stream.
 template <int CH>
 struct HalfTilePixels { uint32_t w[2][2 * CH]; };   // the raw bytes of 8 pixels x 2 rows, in registers
 
@@ -166,13 +110,12 @@ __device__ __forceinline__ HalfTilePixels<CH> load_half_tile(const uint8_t *__re
     return px;
 }
 
-// (A non-inlined variant with both half-tiles' loads issued up front was measured 10 % slower:
-// the call pins the raw pixels in registers across the 460-instruction body.)
 template <int CH>
-__device__ __forceinline__ void convert_half_tile(const HalfTilePixels<CH> px, int bc, int qy, int C, int *__restrict__ planes)
+__device__ __forceinline__ uint32_t convert_half_tile(const HalfTilePixels<CH> px, int bc, int qy, int C, int *__restrict__ planes)
 {
     const uint32_t (&w)[2][2 * CH] = px.w;
     int sb[4], sr[4];
+    uint32_t fmin[4] = { 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu };
     // The four 16-byte luma groups of this strip are chunks i0 .. i0+3 of one block (i0 = 4*(qy & 3)):
     // chunk_word(blk, i0 + n) == a1 ^ (n << 2), one LOP3 per store instead of the full swizzle.
     const int by = qy >> 2, blk = by * 2 * C + bc, i0 = (qy & 3) << 2;
@@ -185,9 +128,9 @@ __device__ __forceinline__ void convert_half_tile(const HalfTilePixels<CH> px, i
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int i = 4 * j + e;              // pixel 0..7 of the row
+                const int byte0 = CH * i, wi = byte0 >> 2, sh = byte0 & 3;
                 int cb, cr;
-                ycbcr_from_doubles(M1_ROW_BYTE_D(w[dy], CH * i), M1_ROW_BYTE_D(w[dy], CH * i + 1),
-                                   M1_ROW_BYTE_D(w[dy], CH * i + 2), yv[e], cb, cr);
+                colour_int_pixel(w[dy][wi], w[dy][wi + 1 < 2 * CH ? wi + 1 : wi], sh, yv[e], cb, cr, fmin[i >> 1]);
                 if (dy == 0 && (e & 1) == 0) { sb[i >> 1] = cb; sr[i >> 1] = cr; }
                 else                         { sb[i >> 1] += cb; sr[i >> 1] += cr; }
             }
@@ -198,13 +141,39 @@ __device__ __forceinline__ void convert_half_tile(const HalfTilePixels<CH> px, i
     const int kc = (6 * k + 4) & 7;                   // key of the Cb block; the Cr block (thread + 1) has kc ^ 1
     *(int4 *)(planes + chunk_word_keyed(4 * C + k, qy * 2 + h, kc)) = make_int4(sb[0] >> 2, sb[1] >> 2, sb[2] >> 2, sb[3] >> 2);
     *(int4 *)(planes + chunk_word_keyed(5 * C + k, qy * 2 + h, kc ^ 1)) = make_int4(sr[0] >> 2, sr[1] >> 2, sr[2] >> 2, sr[3] >> 2);
+    uint32_t flags = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) flags |= (fmin[q] < M1_COLOUR_FLAG_LIMIT ? 1u : 0u) << q;
+    return flags;
 }
 
 template <int CH>
-__device__ __forceinline__ void color_half_tile(const uint8_t *__restrict__ row0, size_t pitch, int bc, int qy,
-                                                int C, int *__restrict__ planes)
+__device__ __forceinline__ uint32_t color_half_tile(const uint8_t *__restrict__ row0, size_t pitch, int bc, int qy,
+                                                    int C, int *__restrict__ planes)
 {
-    convert_half_tile<CH>(load_half_tile<CH>(row0, pitch), bc, qy, C, planes);
+    return convert_half_tile<CH>(load_half_tile<CH>(row0, pitch), bc, qy, C, planes);
+}
+
+// One 2x2 pixel quad by the exact double chain: any alignment / channel count, coordinates clamped to
+// the picture (= edge replication up to the coded size).  (x0, y0): top-left pixel of the half-tile,
+// qx: quad 0..3 inside it.  Used by the generic half-tile and by the fix-up pass of the fast path.
+__device__ __forceinline__ void color_quad_exact(const uint8_t *__restrict__ fr, const M1Geom &g, int x0, int y0,
+                                                 int bc, int qy, int qx, int C, int *__restrict__ planes)
+{
+    int sb = 0, sr = 0;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+            const uint8_t *p = px_ptr(fr, g, x0 + 2 * qx + dx, y0 + dy);
+            int yy, cb, cr;
+            ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
+            const int rr = 2 * qy + dy, cc = 2 * qx + dx;
+            planes[plane_word((rr >> 3) * 2 * C + bc, rr & 7, cc, C)] = yy;
+            sb += cb; sr += cr;
+        }
+    planes[plane_word(4 * C + (bc >> 1), qy, 4 * (bc & 1) + qx, C)] = sb >> 2;
+    planes[plane_word(5 * C + (bc >> 1), qy, 4 * (bc & 1) + qx, C)] = sr >> 2;
 }
 
 // Generic half-tile: any alignment / channel count, coordinates clamped to the picture (= edge
@@ -212,22 +181,7 @@ __device__ __forceinline__ void color_half_tile(const uint8_t *__restrict__ row0
 __device__ __noinline__ void color_half_tile_generic(const uint8_t *__restrict__ fr, const M1Geom &g, int x0, int y0,
                                                      int bc, int qy, int C, int *__restrict__ planes)
 {
-    for (int qx = 0; qx < 4; ++qx) {
-        int sb = 0, sr = 0;
-#pragma unroll
-        for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 2; ++dx) {
-                const uint8_t *p = px_ptr(fr, g, x0 + 2 * qx + dx, y0 + dy);
-                int yy, cb, cr;
-                ycbcr_exact(p[0], p[1], p[2], yy, cb, cr);
-                const int rr = 2 * qy + dy, cc = 2 * qx + dx;
-                planes[plane_word((rr >> 3) * 2 * C + bc, rr & 7, cc, C)] = yy;
-                sb += cb; sr += cr;
-            }
-        planes[plane_word(4 * C + (bc >> 1), qy, 4 * (bc & 1) + qx, C)] = sb >> 2;
-        planes[plane_word(5 * C + (bc >> 1), qy, 4 * (bc & 1) + qx, C)] = sr >> 2;
-    }
+    for (int qx = 0; qx < 4; ++qx) color_quad_exact(fr, g, x0, y0, bc, qy, qx, C, planes);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -265,15 +219,22 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     constexpr int kTabVecs = ((int)offsetof(M1Tables, ka) + 15) / 16;
 #pragma unroll 1
     for (int i = tid; i < kTabVecs; i += nthr) ((uint4 *)tb)[i] = __ldg((const uint4 *)gtab + i);
-    win[tid] = 0;
     if (tid < 8) wtot[tid] = 0;
+    // Until the block phase needs it as the bit window, `win` holds the fix-up queue of the integer
+    // colour path: one 16-bit entry per flagged 2x2 pixel quad (a chunk has at most 1024 quads = the
+    // window's 512 words), counted in wtot[4].
+    unsigned short *fixq = (unsigned short *)win;
+    int *fix_cnt = wtot + 4;
 
     const uint8_t *fr = rgb + (size_t)frame * g.frame_stride;
 
     // ---- phase 1: colour conversion into the chunk's planes --------------------------------
+#ifdef M1_EXPERIMENTS
     if (g.debug_skip & 1) {
-        // profiling only: leave the planes as they are
-    } else if (kLoad >= 0) {
+        // profiling only (tools/ build): leave the planes as they are
+    } else
+#endif
+    if (kLoad >= 0) {
         // FULL: slice = macroblock row.  A thread owns the 8-pixel x 4-row strip (block column bc of the
         // chunk, row quad q4) = two half-tiles, so the index split and the pixel address are computed once
         // and stepped by rows; 4 * nbc = 8 * nmb strips <= blockDim.x.
@@ -293,7 +254,14 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h, y += 2) {
                     const size_t rp = (y + 1 <= last) ? pitch : 0;
-                    color_half_tile<kCh>(row, rp, bc, 2 * q4 + h, C, planes);
+                    const uint32_t fl = color_half_tile<kCh>(row, rp, bc, 2 * q4 + h, C, planes);
+                    if (fl) {                                // rare: queue the flagged quads of this half-tile
+                        const int slot = atomicAdd(fix_cnt, __popc(fl));
+                        int k = 0;
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (fl & (1u << q)) fixq[slot + k++] = (unsigned short)((st << 3) | (h << 2) | q);
+                    }
                     row += rp + ((y + 2 <= last) ? pitch : 0);
                 }
             } else {
@@ -325,7 +293,27 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         }
     }
     __syncthreads();
-    if (g.debug_skip & 2) return;                           // profiling only
+    if (kLoad > 0) {
+        // Fix-up pass of the integer colour path: the queued quads again, by the reference's double chain
+        // (their pixels are L1/L2 hits).  One quad per thread, so the cost follows the NUMBER of flagged
+        // quads (about 2 % of them on noise; r == g or g == b pixels are the common causes), not the number of
+        // warps that happen to contain one.
+        const int nfix = *fix_cnt;
+        if (nfix) {
+            const int nbc = 2 * nmb;
+            const unsigned inv = (chunk == g.chunks_per_slice - 1) ? g.inv_nbc[1] : g.inv_nbc[0];
+            for (int e = tid; e < nfix; e += nthr) {
+                const int code = fixq[e], st = code >> 3, h = (code >> 2) & 1, q = code & 3;
+                const int q4 = (int)(((unsigned)st * inv) >> 16), bc = st - q4 * nbc;
+                color_quad_exact(fr, g, 16 * mb0 + 8 * bc, 16 * slice + 4 * q4 + 2 * h, bc, 2 * q4 + h, q, C, planes);
+            }
+            __syncthreads();
+        }
+    }
+    win[tid] = 0;                                           // the queue is consumed: `win` becomes the bit window
+#ifdef M1_EXPERIMENTS
+    if (g.debug_skip & 2) return;                           // profiling only (tools/ build)
+#endif
 
     // ---- phase 2: one thread per 8x8 block, threads in CODING order (t = 6*mb + blk), so the
     // bit offsets are a plain scan over the thread index.  pb = the thread's plane block.
@@ -436,9 +424,6 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     if (tid == 0)
         chunk_bits[(size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk] = (uint32_t)total_bits;
 }
-
-#include "m1cu_encode_ws.cuh"
-#include "m1cu_encode_persist.cuh"
 
 // -------------------------------------------------------------------------------------------
 // k_layout: one CTA per picture.  Slice s starts at a byte boundary (include/encoder.h:442-443);
@@ -720,6 +705,8 @@ __global__ void k_synth_rgb(uint32_t seed, long first_frame, int n_frames, int W
             o[0] = (uint8_t)((255u * x / (uint32_t)W + (n & 15u) + f) & 255u);
             o[1] = (uint8_t)((255u * y / (uint32_t)H + ((n >> 4) & 15u)) & 255u);
             o[2] = (uint8_t)(((x + y) / 8u + ((n >> 8) & 15u) + 2u * f) & 255u);
+            if (kind == 2) { o[1] = o[0]; o[2] = o[0]; }          // grey
+            else if (kind == 3) { o[1] = o[0]; }                   // r == g
         }
     }
 }
@@ -730,7 +717,11 @@ __global__ void k_synth_rgb(uint32_t seed, long first_frame, int n_frames, int W
 size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
 {
     (void)threads;
-    static const size_t pad = getenv("M1_PAD_SMEM") ? (size_t)atoi(getenv("M1_PAD_SMEM")) : 0;   // occupancy experiments
+#ifdef M1_EXPERIMENTS
+    static const size_t pad = (size_t)m1x_env_int("M1_PAD_SMEM");   // occupancy experiments
+#else
+    const size_t pad = 0;
+#endif
     return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 4) * 4 + sizeof(M1Tables) + 8 * sizeof(int) + 16 + pad;
 }
 
@@ -759,19 +750,6 @@ cudaError_t m1k_prepare(const M1Geom &g)
             if (e != cudaSuccess) return e;
         }
     }
-    if (ws_kernel_for(g, false)) {
-        for (bool lv : { false, true }) {
-            cudaError_t e = cudaFuncSetAttribute(ws_kernel_for(g, lv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m1k_ws_smem_bytes());
-            if (e != cudaSuccess) return e;
-        }
-    }
-    if (persist_kernel_for(g, false)) {
-        for (bool lv : { false, true }) {
-            cudaError_t e = cudaFuncSetAttribute(persist_kernel_for(g, lv), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)m1k_persist_smem_bytes(g, m1k_encode_threads(g)));
-            if (e != cudaSuccess) return e;
-        }
-    }
     return cudaSuccess;
 }
 
@@ -779,27 +757,7 @@ cudaError_t m1k_launch_encode(const M1Geom &g, const M1Quant &q, const uint8_t *
                               const M1Tables *tables, uint32_t *staging, uint32_t *chunk_bits,
                               short *levels, int *err, cudaStream_t st)
 {
-    if (ws_kernel_t ws = ws_kernel_for(g, levels != nullptr)) {
-        // persistent warp-specialised kernel: one CTA per residency slot (3 per SM), chunks strided over them
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int n_chunks = g.chunks_per_frame * n_frames;
-        const int grid = n_chunks < 3 * sms ? n_chunks : 3 * sms;
-        ws<<<grid, M1_WS_THREADS, m1k_ws_smem_bytes(), st>>>(g, rgb, tables, n_chunks, staging, chunk_bits, levels, err);
-        return cudaGetLastError();
-    }
     const int threads = m1k_encode_threads(g);
-    if (persist_kernel_t pk = persist_kernel_for(g, levels != nullptr)) {
-        // persistent CTAs (5 per SM), chunks strided over them, next chunk's pixels prefetched by cp.async
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const int n_chunks = g.chunks_per_frame * n_frames;
-        const int grid = n_chunks < 5 * sms ? n_chunks : 5 * sms;
-        pk<<<grid, threads, m1k_persist_smem_bytes(g, threads), st>>>(g, rgb, tables, n_chunks, staging, chunk_bits, levels, err);
-        return cudaGetLastError();
-    }
     const size_t smem = m1k_encode_smem_bytes(g, threads);
     dim3 grid(g.chunks_per_slice, g.slices, n_frames);
     M1NzKeys nk;

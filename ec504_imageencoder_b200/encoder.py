@@ -20,7 +20,7 @@ from . import _native
 
 MODE_FULL = 0        # raster macroblocks, 4:2:0 chroma (BASELINE configs)
 MODE_REF_COMPAT = 1  # literal traversal of include/encoder.h:238-443 (drop-in byte parity)
-SYNTH_NATURAL, SYNTH_NOISE = 0, 1
+SYNTH_NATURAL, SYNTH_NOISE, SYNTH_GREY, SYNTH_RG_EQUAL = 0, 1, 2, 3
 DEFAULT_QUALITY = 12  # reference main.c:16
 
 _ERRORS = {-1: "bad argument", -2: "CUDA failure / no device", -3: "output capacity",
@@ -65,7 +65,8 @@ class M1Encoder:
     """One context per GPU.  Geometry and quality are fixed at construction."""
 
     def __init__(self, width: int, height: int, channels: int = 3, mode: int = MODE_FULL,
-                 quality: int = DEFAULT_QUALITY, max_frames: int = 64, device: int | None = None):
+                 quality: int = DEFAULT_QUALITY, max_frames: int = 64, device: int | None = None,
+                 chunk_mbs: int = 0, chunk_even: bool = False, win_words: int = 0):
         self.lib = _native.m1cu()
         if self.lib.m1cu_device_count() == 0 or not torch.cuda.is_available():
             raise M1Error(-2, "no CUDA device: the encode path has no CPU fallback")
@@ -73,8 +74,10 @@ class M1Encoder:
         self.width, self.height, self.channels = int(width), int(height), int(channels)
         self.mode, self.quality, self.max_frames = int(mode), int(quality), int(max_frames)
         h = C.c_void_p()
-        rc = self.lib.m1cu_create(C.byref(h), self.device, self.width, self.height, self.channels,
-                                  self.mode, self.quality, self.max_frames)
+        # work-partition knobs (m1cu_tuning; tests and sweeps only, no effect on the bytes)
+        tuning = (C.c_int * 3)(int(chunk_mbs), int(bool(chunk_even)), int(win_words))
+        rc = self.lib.m1cu_create_ex(C.byref(h), self.device, self.width, self.height, self.channels,
+                                     self.mode, self.quality, self.max_frames, tuning)
         if rc != 0:
             raise M1Error(rc, (self.lib.m1cu_last_error(None) or b"").decode())
         self._h = h

@@ -59,7 +59,9 @@ enum m1cu_status {
                                 encode_blk_coeff (source/vlc.c:383) and crashes; we report it   */
 };
 
-enum m1cu_synth_kind { M1CU_SYNTH_NATURAL = 0, M1CU_SYNTH_NOISE = 1 };
+enum m1cu_synth_kind { M1CU_SYNTH_NATURAL = 0, M1CU_SYNTH_NOISE = 1,
+                       M1CU_SYNTH_GREY = 2,      /* natural's R channel in all three: every pixel is an exact-quotient case */
+                       M1CU_SYNTH_RG_EQUAL = 3   /* natural with G := R                                                   */ };
 
 typedef struct m1cu_ctx m1cu_ctx;
 
@@ -75,6 +77,15 @@ const char *m1cu_last_error(const m1cu_ctx *ctx);          /* ctx may be NULL: l
  * max_frames: the largest n_frames a single encode call will be given (sizes the staging). */
 int  m1cu_create(m1cu_ctx **out, int device, int width, int height, int channels,
                  int mode, int quality_factor, int max_frames);
+/* Same, with the kernel's work partition chosen by the caller (tests and tuning sweeps; NULL or zero
+ * fields = defaults).  None of the fields changes a result byte. */
+typedef struct m1cu_tuning {
+    int chunk_mbs;   /* macroblocks per CTA, 1..16 (default 16: full chunks + one shorter tail per slice) */
+    int chunk_even;  /* != 0: equal chunks per slice instead                                            */
+    int win_words;   /* shared-memory bit-window words per pass, 4..512 (default 512)                   */
+} m1cu_tuning;
+int  m1cu_create_ex(m1cu_ctx **out, int device, int width, int height, int channels,
+                    int mode, int quality_factor, int max_frames, const m1cu_tuning *tuning);
 int  m1cu_destroy(m1cu_ctx *ctx);
 int  m1cu_set_stream(m1cu_ctx *ctx, void *cuda_stream);    /* cudaStream_t; NULL = own stream   */
 int  m1cu_synchronize(m1cu_ctx *ctx);

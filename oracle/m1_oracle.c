@@ -537,6 +537,10 @@ void m1o_synth_rgb(uint32_t seed, long frame_index, int W, int H, int kind, uint
                 p[0] = (uint8_t)((255u * (uint32_t)x / (uint32_t)W + (n & 15u) + f) & 255u);
                 p[1] = (uint8_t)((255u * (uint32_t)y / (uint32_t)H + ((n >> 4) & 15u)) & 255u);
                 p[2] = (uint8_t)((((uint32_t)x + (uint32_t)y) / 8u + ((n >> 8) & 15u) + 2u * f) & 255u);
+                /* worst cases of an integer colour path (every pixel an exact-quotient exception of
+                 * source/image_processing.c:104-106): grey pictures, and pictures with r == g */
+                if (kind == M1O_SYNTH_GREY) { p[1] = p[0]; p[2] = p[0]; }
+                else if (kind == M1O_SYNTH_RG_EQUAL) { p[1] = p[0]; }
             }
         }
     }

@@ -4,6 +4,7 @@
 // Not part of libm1cu.so and not a fallback: the product has no host encode path.
 #include "../../ec504_imageencoder_b200/csrc/m1cu_block.cuh"
 #include "../../ec504_imageencoder_b200/csrc/m1cu_quant.h"
+#include "../../ec504_imageencoder_b200/csrc/m1cu_colour.cuh"
 #include <string.h>
 
 namespace {
@@ -90,6 +91,53 @@ int m1bh_code_levels(const int32_t zz[64], int is_luma, int tid, int key, char *
     StrSink ss{bits, cap, 0};
     code_block(ss, rec, tid, nz, is_luma != 0, &g_tb, key);
     return ss.n;
+}
+
+// The kernels' integer colour path (m1cu_colour.cuh) over ALL 2^24 colours, in each of the four byte
+// alignments a 3-byte pixel can have inside 32-bit words (neighbouring bytes filled with `junk`, which
+// the zero coefficients must ignore).  The claim the kernel relies on: an UNFLAGGED pixel's three
+// quotients equal the reference's double chain.  Returns the number of violations (must be 0).
+// stats: [0] flagged colours (alignment 0), [1..3] colours whose double chain differs from the integer
+// quotient for Y / Cb / Cr (all of them must be flagged), [4] flagged colours whose quotients were right.
+long m1bh_colour_sweep(unsigned junk, long long stats[5])
+{
+    long bad = 0;
+    for (int i = 0; i < 5; ++i) stats[i] = 0;
+    const uint32_t J = (junk & 0xffu) * 0x01010101u;
+    for (int r = 0; r < 256; ++r)
+        for (int g = 0; g < 256; ++g)
+            for (int b = 0; b < 256; ++b) {
+                int ye, cbe, cre;
+                ycbcr_exact_host(r, g, b, ye, cbe, cre);
+                for (int sh = 0; sh < 4; ++sh) {
+                    // bytes sh, sh+1, sh+2 of the 8-byte window (w0 low word) hold r, g, b
+                    unsigned long long win = ((unsigned long long)J << 32) | J;
+                    win &= ~(0xffffffull << (8 * sh));
+                    win |= ((unsigned long long)r | ((unsigned long long)g << 8) | ((unsigned long long)b << 16)) << (8 * sh);
+                    int y, cb, cr;
+                    uint32_t fm = 0xffffffffu;
+                    colour_int_pixel((uint32_t)win, (uint32_t)(win >> 32), sh, y, cb, cr, fm);
+                    const bool flagged = fm < M1_COLOUR_FLAG_LIMIT;
+                    const bool same = y == ye && cb == cbe && cr == cre;
+                    if (!flagged && !same) ++bad;
+                    if (sh == 0) {
+                        stats[0] += flagged;
+                        stats[1] += y != ye; stats[2] += cb != cbe; stats[3] += cr != cre;
+                        stats[4] += flagged && same;
+                    }
+                }
+            }
+    return bad;
+}
+
+// the harness's own double chain for an array of pixels (checked against the oracle by the test)
+void m1bh_ycbcr_exact(const unsigned char *rgb, long n, unsigned char *y, unsigned char *cb, unsigned char *cr)
+{
+    for (long i = 0; i < n; ++i) {
+        int a, b, c;
+        ycbcr_exact_host(rgb[3 * i], rgb[3 * i + 1], rgb[3 * i + 2], a, b, c);
+        y[i] = (unsigned char)a; cb[i] = (unsigned char)b; cr[i] = (unsigned char)c;
+    }
 }
 
 }  // extern "C"

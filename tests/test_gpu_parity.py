@@ -10,7 +10,7 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 import oracle  # noqa: E402
-from oracle import MODE_FULL, MODE_REF_COMPAT, SYNTH_NATURAL, SYNTH_NOISE  # noqa: E402
+from oracle import MODE_FULL, MODE_REF_COMPAT, SYNTH_NATURAL, SYNTH_NOISE, SYNTH_GREY, SYNTH_RG_EQUAL  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -105,6 +105,31 @@ def test_color_all_2_24(m1, port):
     assert np.array_equal(Y.cpu().numpy().ravel(), oy)
     assert np.array_equal(Cb.cpu().numpy().ravel(), ocb)
     assert np.array_equal(Cr.cpu().numpy().ravel(), ocr)
+
+
+def test_encode_kernel_all_colours_all_alignments(m1, port):
+    """All 2^24 colours through k_encode_chunks' integer colour path + fix-up queue (not through the
+    plane kernel): four 4096x4096 pictures holding every colour once, shifted by 0..3 pixels so that every
+    colour meets each of the four byte alignments of a packed 3-byte pixel.  Quality 89: the finest
+    quantiser the reference can encode keeps single-sample errors visible in the levels."""
+    g = np.arange(1 << 24, dtype=np.uint32)
+    base = np.stack([g >> 16, (g >> 8) & 255, g & 255], axis=1).astype(np.uint8)
+    enc = m1.M1Encoder(4096, 4096, 3, MODE_FULL, 89, max_frames=1)
+    for shift in range(4):
+        img = np.ascontiguousarray(np.roll(base, shift, axis=0).reshape(1, 4096, 4096, 3))
+        res = enc.encode_device(torch.from_numpy(img).cuda(), want_levels=True)
+        rp, rl = port.encode_picture(img[0], 89, MODE_FULL, want_levels=True)
+        assert np.array_equal(res.levels[0].cpu().numpy(), rl), f"levels differ (shift {shift})"
+        assert res.payloads()[0] == rp, f"payload differs (shift {shift})"
+    enc.close()
+
+
+@pytest.mark.parametrize("kind", [SYNTH_GREY, SYNTH_RG_EQUAL])
+@pytest.mark.parametrize("W,H,q", [(352, 240, 12), (1920, 1080, 50), (100, 70, 89)])
+def test_fixup_queue_worst_cases(m1, port, kind, W, H, q):
+    """Grey and r == g pictures: every 2x2 quad of every chunk is queued for the exact recomputation
+    (the queue is exactly as large as a chunk has quads)."""
+    _encode_both(m1, port, W, H, 2, q, kind)
 
 
 @pytest.mark.parametrize("channels", [3, 4])
