@@ -38,10 +38,14 @@ $(STBOBJ): $(STB_IMAGE_H)
 	$(CC) -O2 -fPIC -w -x c -DSTB_IMAGE_IMPLEMENTATION -c $(STB_IMAGE_H) -o $@
 endif
 STBLINK := $(if $(wildcard $(STB_IMAGE_H))$(wildcard $(STBOBJ)),$(STBOBJ),)
+ifeq ($(STBLINK),)
+$(warning *** stb_image.h not found at STB_IMAGE_H=$(STB_IMAGE_H): libencoder.so is being built WITHOUT a JPEG decoder.)
+$(warning *** mpeg_encode_procedure() will load no picture and return -1; pass STB_IMAGE_H=/path/to/stb_image.h (v2.30, public domain).)
+endif
 
 sharedlib: $(PKG)/libencoder.so
 $(PKG)/libencoder.so: $(HOSTOBJ) $(STBLINK) $(PKG)/libm1cu.so
-	$(CC) -shared -o $@ $(HOSTOBJ) $(STBLINK) -L$(PKG) -lm1cu -Wl,-rpath,'$$ORIGIN' -lm
+	$(CC) -shared -o $@ $(HOSTOBJ) $(STBLINK) -L$(PKG) -lm1cu -Wl,-rpath,'$$ORIGIN' -lm -lpthread
 	ln -sf $(PKG)/libencoder.so libencoder.so
 
 encoder: main.c $(PKG)/libencoder.so

@@ -90,6 +90,7 @@ def m1cu() -> C.CDLL:
         "m1cu_check": (C.c_int, [vp]),
         "m1cu_encode_host": (C.c_int, [vp, u8p, C.c_int, u8p, C.c_size_t, u32p, i16p, C.POINTER(C.c_size_t)]),
         "m1cu_ycbcr_planes": (C.c_int, [vp, u8p, u8p, u8p, u8p]),
+        "m1cu_host_batch_planes": (C.c_int, [vp, C.c_int, u8p, C.c_size_t]),
         "m1cu_synth_rgb": (C.c_int, [vp, C.c_uint32, C.c_long, C.c_int, C.c_int, u8p]),
         "m1cu_launch_count": (C.c_ulonglong, [vp]),
         "m1cu_enable_timing": (C.c_int, [vp, C.c_int]),
@@ -119,7 +120,7 @@ M1CU_SYMBOLS = (
     "m1cu_abi_version", "m1cu_device_count", "m1cu_qmatrix", "m1cu_last_error", "m1cu_create", "m1cu_create_ex",
     "m1cu_destroy", "m1cu_set_stream", "m1cu_synchronize", "m1cu_macroblocks_per_frame",
     "m1cu_frame_bytes_in", "m1cu_payload_bound", "m1cu_typical_out_bytes", "m1cu_encode_device",
-    "m1cu_check", "m1cu_encode_host", "m1cu_ycbcr_planes", "m1cu_synth_rgb", "m1cu_launch_count",
+    "m1cu_check", "m1cu_encode_host", "m1cu_ycbcr_planes", "m1cu_host_batch_planes", "m1cu_synth_rgb", "m1cu_launch_count",
     "m1cu_enable_timing", "m1cu_kernel_times",
     "m1cu_device_alloc", "m1cu_device_free", "m1cu_pinned_alloc", "m1cu_pinned_free",
     "m1cu_memcpy_h2d", "m1cu_memcpy_d2h",

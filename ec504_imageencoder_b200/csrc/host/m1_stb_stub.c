@@ -6,3 +6,4 @@ __attribute__((weak)) unsigned char *stbi_load(char const *f, int *x, int *y, in
 { (void)f; (void)x; (void)y; (void)c; (void)d; return NULL; }
 __attribute__((weak)) void stbi_image_free(void *p) { (void)p; }
 __attribute__((weak)) const char *stbi_failure_reason(void) { return "libencoder was built without stb_image.h"; }
+__attribute__((weak)) int stbi_info(char const *f, int *x, int *y, int *c) { (void)f; (void)x; (void)y; (void)c; return 0; }

@@ -54,7 +54,8 @@ struct m1cu_ctx {
     unsigned long long *d_running = nullptr;
     unsigned int *d_done = nullptr;
     // host-path scratch
-    uint8_t *d_in = nullptr;   size_t d_in_cap = 0;
+    uint8_t *d_in = nullptr;   size_t d_in_cap = 0;  int d_in_frames = 0;   // pictures the last host-buffer call uploaded
+    uint8_t *d_planes = nullptr; size_t d_planes_cap = 0;                      // m1cu_host_batch_planes
     uint8_t *d_out = nullptr;  size_t d_out_cap = 0;
     uint32_t *d_fbytes = nullptr; unsigned long long *d_foff = nullptr; int d_meta_frames = 0;
     int16_t *d_levels = nullptr; size_t d_levels_cap = 0;
@@ -267,7 +268,7 @@ int m1cu_destroy(m1cu_ctx *ctx)
     cudaFree(ctx->d_staging); cudaFree(ctx->d_chunk_bits); cudaFree(ctx->d_chunk_dst);
     cudaFree(ctx->d_tables); cudaFree(ctx->d_stream_tmpl); cudaFree(ctx->d_seg_off); cudaFree(ctx->d_stream); cudaFree(ctx->d_stream_end); cudaFree(ctx->d_err); cudaFree(ctx->d_running); cudaFree(ctx->d_done);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_fbytes); cudaFree(ctx->d_foff);
-    cudaFree(ctx->d_levels);
+    cudaFree(ctx->d_levels); cudaFree(ctx->d_planes);
     if (ctx->h_out) cudaFreeHost(ctx->h_out);
     if (ctx->h_fbytes) cudaFreeHost(ctx->h_fbytes);
     if (ctx->h_foff) cudaFreeHost(ctx->h_foff);
@@ -383,14 +384,34 @@ int m1cu_check(m1cu_ctx *ctx)
 // Every sub-batch owns a fixed region of d_out, so nothing has to be known on the host before the
 // next launch.  Returns M1CU_ERR_CAPACITY when a region overflows (the caller then takes the simple
 // path with worst-case sizing).
+enum { M1_INTERNAL_REGION_OVERFLOW = -100 };   // never leaves this file: a sub-batch's payload region was too small
+
+static int encode_host_pipelined_impl(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, uint8_t *h_out, size_t out_cap,
+                                      uint32_t *h_frame_bytes, size_t *total_bytes, int S);
+
+// Every exit leaves no copy in flight on the side streams: the caller may reuse or free h_rgb / h_out.
 static int encode_host_pipelined(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, uint8_t *h_out, size_t out_cap,
+                                 uint32_t *h_frame_bytes, size_t *total_bytes, int S)
+{
+    const int rc = encode_host_pipelined_impl(ctx, h_rgb, n_frames, h_out, out_cap, h_frame_bytes, total_bytes, S);
+    if (rc != M1CU_OK) {
+        if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream);
+        if (ctx->back_stream) cudaStreamSynchronize(ctx->back_stream);
+    }
+    return rc;
+}
+
+static int encode_host_pipelined_impl(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, uint8_t *h_out, size_t out_cap,
                                  uint32_t *h_frame_bytes, size_t *total_bytes, int S)
 {
     const M1Geom &g = ctx->g;
     const int nsub = (n_frames + S - 1) / S;
     const size_t region = m1cu_typical_out_bytes(ctx, S);
     int rc;
+    ctx->d_in_frames = 0;
     if ((rc = ensure(ctx, (void **)&ctx->d_in, &ctx->d_in_cap, (size_t)g.frame_stride * n_frames))) return rc;
+    ctx->d_in_frames = n_frames;
     if ((rc = ensure(ctx, (void **)&ctx->d_out, &ctx->d_out_cap, region * nsub))) return rc;
     if ((rc = ensure(ctx, (void **)&ctx->h_out, &ctx->h_out_cap, region * nsub, true))) return rc;
     if (ctx->pipe_sub < nsub || ctx->pipe_frames < n_frames) {
@@ -461,8 +482,9 @@ static int encode_host_pipelined(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_fram
         }
     }
     rc = m1cu_check(ctx);                                      // device-side flags of all sub-batches
+    if (rc == M1CU_ERR_CAPACITY) return fail(ctx, M1_INTERNAL_REGION_OVERFLOW, "payload region of a sub-batch overflowed");
     if (rc) return rc;
-    if (flags) return fail(ctx, M1CU_ERR_CAPACITY, "payload region of a sub-batch overflowed");
+    if (flags) return fail(ctx, M1_INTERNAL_REGION_OVERFLOW, "payload region of a sub-batch overflowed");
     CU(cudaStreamSynchronize(ctx->back_stream));
     if ((rc = compact(nsub - 1))) return fail(ctx, rc, "m1cu_encode_host: h_out too small");
     if (total_bytes) *total_bytes = pos;
@@ -484,14 +506,15 @@ int m1cu_encode_host(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, uint8_t 
         if (S < 1) S = 1;
         if (!h_levels && n_frames >= 3 * S) {
             const int prc = encode_host_pipelined(ctx, h_rgb, n_frames, h_out, out_cap, h_frame_bytes, total_bytes, S);
-            if (prc != M1CU_ERR_CAPACITY) return prc;
-            CU(cudaDeviceSynchronize());                       // rare: fall through to worst-case sizing below
-            m1cu_check(ctx);
+            if (prc != M1_INTERNAL_REGION_OVERFLOW) return prc; // includes M1CU_ERR_CAPACITY: the caller's h_out is too small
+            m1cu_check(ctx);                                   // rare: clear the flag, fall through to worst-case sizing below
         }
     }
     const size_t in_bytes = (size_t)g.frame_stride * n_frames;
     int rc;
+    ctx->d_in_frames = 0;
     if ((rc = ensure(ctx, (void **)&ctx->d_in, &ctx->d_in_cap, in_bytes))) return rc;
+    ctx->d_in_frames = n_frames;
     if (ctx->d_meta_frames < n_frames) {
         cudaFree(ctx->d_fbytes); cudaFree(ctx->d_foff); ctx->d_fbytes = nullptr; ctx->d_foff = nullptr;
         if (ctx->h_fbytes) cudaFreeHost(ctx->h_fbytes);
@@ -545,8 +568,30 @@ int m1cu_ycbcr_planes(m1cu_ctx *ctx, const uint8_t *d_rgb, uint8_t *d_y, uint8_t
 {
     if (!ctx || !d_rgb || !d_y || !d_cb || !d_cr) return fail(ctx, M1CU_ERR_ARG, "m1cu_ycbcr_planes: bad argument");
     CU(cudaSetDevice(ctx->device));
-    CU(m1k_launch_planes(d_rgb, ctx->g.channels, (size_t)ctx->g.W * ctx->g.H, d_y, d_cb, d_cr, ctx->stream));
+    CU(m1k_launch_planes(d_rgb, ctx->g.channels, (size_t)ctx->g.W * ctx->g.H, 1, 0, 0, d_y, d_cb, d_cr, ctx->stream));
     ctx->launches += 1;
+    return M1CU_OK;
+}
+
+// The .bit side files of a whole batch (source/image_processing.c:753-787, include/encoder.h:460-465)
+// from the pictures the last host-buffer encode call left resident on the device: one launch, one
+// download, no second upload.  h_planes receives per picture Y, Cb, Cr (width*height bytes each).
+int m1cu_host_batch_planes(m1cu_ctx *ctx, int n_frames, uint8_t *h_planes, size_t cap)
+{
+    if (!ctx || !h_planes || n_frames <= 0) return fail(ctx, M1CU_ERR_ARG, "m1cu_host_batch_planes: bad argument");
+    if (n_frames > ctx->d_in_frames || !ctx->d_in)
+        return fail(ctx, M1CU_ERR_ARG, "m1cu_host_batch_planes: more pictures than the last host-buffer encode call uploaded");
+    const size_t npix = (size_t)ctx->g.W * ctx->g.H, need = 3 * npix * (size_t)n_frames;
+    if (cap < need) return fail(ctx, M1CU_ERR_CAPACITY, "m1cu_host_batch_planes: h_planes too small");
+    CU(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = ensure(ctx, (void **)&ctx->d_planes, &ctx->d_planes_cap, need))) return rc;
+    cudaStream_t st = ctx->stream;
+    CU(m1k_launch_planes(ctx->d_in, ctx->g.channels, npix, n_frames, (size_t)ctx->g.frame_stride, 3 * npix,
+                         ctx->d_planes, ctx->d_planes + npix, ctx->d_planes + 2 * npix, st));
+    ctx->launches += 1;
+    CU(cudaMemcpyAsync(h_planes, ctx->d_planes, need, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return M1CU_OK;
 }
 
@@ -693,7 +738,9 @@ int m1cu_encode_host_stream(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames, l
     cudaStream_t st = ctx->stream;
     const size_t in_bytes = (size_t)g.frame_stride * n_frames;
     int rc;
+    ctx->d_in_frames = 0;
     if ((rc = ensure(ctx, (void **)&ctx->d_in, &ctx->d_in_cap, in_bytes))) return rc;
+    ctx->d_in_frames = n_frames;
     if (ctx->d_meta_frames < n_frames) {
         cudaFree(ctx->d_fbytes); cudaFree(ctx->d_foff); ctx->d_fbytes = nullptr; ctx->d_foff = nullptr;
         if (ctx->h_fbytes) cudaFreeHost(ctx->h_fbytes);

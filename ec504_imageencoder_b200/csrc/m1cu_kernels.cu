@@ -219,12 +219,16 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     constexpr int kTabVecs = ((int)offsetof(M1Tables, ka) + 15) / 16;
 #pragma unroll 1
     for (int i = tid; i < kTabVecs; i += nthr) ((uint4 *)tb)[i] = __ldg((const uint4 *)gtab + i);
-    if (tid < 8) wtot[tid] = 0;
-    // Until the block phase needs it as the bit window, `win` holds the fix-up queue of the integer
-    // colour path: one 16-bit entry per flagged 2x2 pixel quad (a chunk has at most 1024 quads = the
-    // window's 512 words), counted in wtot[4].
-    unsigned short *fixq = (unsigned short *)win;
-    int *fix_cnt = wtot + 4;
+    // Until the block phase needs it as the bit window, `win` holds the fix-up queues of the integer
+    // colour path: one 16-bit entry per flagged 2x2 pixel quad, one queue of 256 entries per warp (a
+    // warp's 32 strips hold 256 quads; 4 queues = the window's 512 words), counted in wtot[4 + warp].
+    // Queue and counter are private to the warp until the barrier, so zeroing the counter needs no
+    // CTA-wide barrier of its own.
+    unsigned short *fixq = (unsigned short *)win + 256 * (tid >> 5);
+    int *fix_cnt = wtot + 4 + (tid >> 5);
+    if ((tid & 31) == 0) { wtot[tid >> 5] = 0; *fix_cnt = 0; }
+    if (tid < 4 && tid >= (nthr >> 5)) { wtot[tid] = 0; wtot[4 + tid] = 0; }   // warps this CTA does not have
+    __syncwarp();
 
     const uint8_t *fr = rgb + (size_t)frame * g.frame_stride;
 
@@ -298,12 +302,15 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         // (their pixels are L1/L2 hits).  One quad per thread, so the cost follows the NUMBER of flagged
         // quads (about 2 % of them on noise; r == g or g == b pixels are the common causes), not the number of
         // warps that happen to contain one.
-        const int nfix = *fix_cnt;
+        const int4 fc = *(const int4 *)(wtot + 4);          // queue lengths of the (at most four) warps
+        const int nfix = fc.x + fc.y + fc.z + fc.w;
         if (nfix) {
             const int nbc = 2 * nmb;
             const unsigned inv = (chunk == g.chunks_per_slice - 1) ? g.inv_nbc[1] : g.inv_nbc[0];
             for (int e = tid; e < nfix; e += nthr) {
-                const int code = fixq[e], st = code >> 3, h = (code >> 2) & 1, q = code & 3;
+                int qi = e, qw = 0;                         // entry qi of warp qw's queue
+                if (qi >= fc.x) { qi -= fc.x; qw = 1; if (qi >= fc.y) { qi -= fc.y; qw = 2; if (qi >= fc.z) { qi -= fc.z; qw = 3; } } }
+                const int code = ((const unsigned short *)win)[256 * qw + qi], st = code >> 3, h = (code >> 2) & 1, q = code & 3;
                 const int q4 = (int)(((unsigned)st * inv) >> 16), bc = st - q4 * nbc;
                 color_quad_exact(fr, g, 16 * mb0 + 8 * bc, 16 * slice + 4 * q4 + 2 * h, bc, 2 * q4 + h, q, C, planes);
             }
@@ -571,9 +578,12 @@ k_stitch(const __grid_constant__ M1Geom g, const uint32_t *__restrict__ staging,
 // Full-resolution planes (the .bit side files, source/image_processing.c:753-787) and the
 // synthetic generator (the test oracle restates the same integer formula).
 // -------------------------------------------------------------------------------------------
-__global__ void k_ycbcr_planes(const uint8_t *__restrict__ rgb, int channels, size_t npix,
-                               uint8_t *__restrict__ Y, uint8_t *__restrict__ Cb, uint8_t *__restrict__ Cr)
+// blockIdx.y = picture: picture f's planes are Y, Cb, Cr + f * plane_stride, its pixels rgb + f * frame_stride.
+__global__ void k_ycbcr_planes(const uint8_t *__restrict__ rgb, int channels, size_t npix, size_t frame_stride,
+                               size_t plane_stride, uint8_t *__restrict__ Y, uint8_t *__restrict__ Cb, uint8_t *__restrict__ Cr)
 {
+    const size_t f = blockIdx.y;
+    rgb += f * frame_stride; Y += f * plane_stride; Cb += f * plane_stride; Cr += f * plane_stride;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < npix; i += (size_t)gridDim.x * blockDim.x) {
         const uint8_t *p = rgb + i * channels;
         int y, cb, cr;
@@ -786,11 +796,12 @@ cudaError_t m1k_launch_stitch(const M1Geom &g, int n_frames, int blocks_x, const
     return cudaGetLastError();
 }
 
-cudaError_t m1k_launch_planes(const uint8_t *rgb, int channels, size_t npix, uint8_t *Y, uint8_t *Cb, uint8_t *Cr,
-                              cudaStream_t st)
+cudaError_t m1k_launch_planes(const uint8_t *rgb, int channels, size_t npix, int n_frames, size_t frame_stride,
+                              size_t plane_stride, uint8_t *Y, uint8_t *Cb, uint8_t *Cr, cudaStream_t st)
 {
     const int blocks = (int)((npix + 255) / 256 < 148 * 8 ? (npix + 255) / 256 : 148 * 8);
-    k_ycbcr_planes<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(rgb, channels, npix, Y, Cb, Cr);
+    dim3 grid(blocks > 0 ? blocks : 1, n_frames);
+    k_ycbcr_planes<<<grid, 256, 0, st>>>(rgb, channels, npix, frame_stride, plane_stride, Y, Cb, Cr);
     return cudaGetLastError();
 }
 

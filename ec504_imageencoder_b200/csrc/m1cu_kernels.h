@@ -18,8 +18,8 @@ cudaError_t m1k_launch_stitch(const M1Geom &g, int n_frames, int blocks_x, const
                               const uint32_t *chunk_bits, const uint32_t *chunk_dst,
                               const uint32_t *frame_bytes, const unsigned long long *frame_off,
                               uint8_t *out, unsigned long long out_cap, cudaStream_t st);
-cudaError_t m1k_launch_planes(const uint8_t *rgb, int channels, size_t npix, uint8_t *Y, uint8_t *Cb, uint8_t *Cr,
-                              cudaStream_t st);
+cudaError_t m1k_launch_planes(const uint8_t *rgb, int channels, size_t npix, int n_frames, size_t frame_stride,
+                              size_t plane_stride, uint8_t *Y, uint8_t *Cb, uint8_t *Cr, cudaStream_t st);
 cudaError_t m1k_launch_synth(uint32_t seed, long first_frame, int n_frames, int W, int H, int kind,
                              uint8_t *rgb, cudaStream_t st);
 cudaError_t m1k_launch_push(uint8_t *dst, const uint8_t *src, const unsigned long long *end, unsigned long long cap,

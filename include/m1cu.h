@@ -127,6 +127,12 @@ int m1cu_encode_host(m1cu_ctx *ctx, const uint8_t *h_rgb, int n_frames,
  * files, source/image_processing.c:753-787).  Device pointers, width*height bytes each. */
 int m1cu_ycbcr_planes(m1cu_ctx *ctx, const uint8_t *d_rgb, uint8_t *d_y, uint8_t *d_cb, uint8_t *d_cr);
 
+/* The same planes for the first n_frames pictures of the LAST m1cu_encode_host / m1cu_encode_host_stream call,
+ * computed from the copy of the input that call left on the device: one launch and one download per batch,
+ * no second upload.  h_planes (capacity cap >= 3*width*height*n_frames) receives per picture Y, Cb, Cr.
+ * Synchronous.  What mpeg_encode_procedure uses for the image_%d.bit files (include/encoder.h:460-465). */
+int m1cu_host_batch_planes(m1cu_ctx *ctx, int n_frames, uint8_t *h_planes, size_t cap);
+
 /* ---- utilities used by tests and bench.py -------------------------------------------------- */
 /* Seeded synthetic RGB written straight into device memory (3 bytes per pixel), frames
  * first_frame .. first_frame + n_frames - 1.  Same integer formula as oracle/m1_oracle.c. */

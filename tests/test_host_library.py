@@ -218,8 +218,9 @@ def test_mpeg_encode_procedure_return_codes(host, tmp_path):
     v = tmp_path / "v.mpeg"
     assert host.mpeg_encode_procedure(str(tmp_path / "imgs"), str(tmp_path / "bs"), str(v)) == 0
     assert (tmp_path / "imgs").is_dir() and (tmp_path / "bs").is_dir() and v.stat().st_size == 27
-    # empty images folder -> -1 (:175-183)
+    # empty images folder -> -1 (:175-183); the reference has written the 27-byte pack + system header by then (:85-89)
     assert host.mpeg_encode_procedure(str(tmp_path / "imgs"), str(tmp_path / "bs"), str(v)) == -1
+    assert v.stat().st_size == 27
 
 
 def test_decode_helpers_against_reference(host):
@@ -318,3 +319,87 @@ def test_mpeg_encode_procedure_on_a_jpeg_folder(host, port, tmp_path):
     finally:
         del os.environ["M1_MODE"]
     assert video.read_bytes() == port.encode_stream(frames, 12, 0)
+
+
+def _read_folder(L, folder, W, H):
+    """The stb-decoded pictures of a folder in readdir order (what the driver sees); undecodable files skipped."""
+    class Img(C.Structure):
+        _fields_ = [("width", C.c_int), ("height", C.c_int), ("channels", C.c_int), ("data", C.POINTER(C.c_ubyte))]
+    L.read_jpeg.restype = C.POINTER(Img)
+    L.read_jpeg.argtypes = [C.c_char_p]
+    L.free_image.argtypes = [C.POINTER(Img)]
+    frames = []
+    for name in os.listdir(folder):
+        if ".jpg" not in name and ".jpeg" not in name:
+            continue
+        p = L.read_jpeg(os.path.join(str(folder), name).encode())
+        if not p:
+            continue
+        assert (p.contents.width, p.contents.height, p.contents.channels) == (W, H, 3)
+        frames.append(np.ctypeslib.as_array(p.contents.data, shape=(H, W, 3)).copy())
+        L.free_image(p)
+    return np.stack(frames)
+
+
+@pytest.mark.gpu
+def test_folder_pipeline_multi_batch_and_legacy_path(host, port, tmp_path, monkeypatch):
+    """mpeg_encode_procedure decodes on worker threads into a two-slot pinned ring
+    while the GPU encodes the previous batch.  600 small pictures = three ring turns; the bytes of the
+    video and of every image_N.bit equal the oracle's and equal the decode-everything-first path
+    (M1_DECODE_THREADS=0, the reference's order of work), also with a file stb cannot decode in the
+    folder (skipped, as the reference skips it) and with one of a different size (-1, 27-byte file)."""
+    torch = pytest.importorskip("torch")
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    PIL = pytest.importorskip("PIL.Image")
+    L = host.lib()
+    imgs = tmp_path / "images"
+    imgs.mkdir()
+    rng = np.random.default_rng(11)
+    W, H, N = 64, 48, 600
+    for i in range(N):
+        a = (np.add.outer(np.arange(H) * 3 + i, np.arange(W) * 2)[..., None] + rng.integers(0, 40, (H, W, 3))) % 256
+        PIL.fromarray(a.astype(np.uint8)).save(str(imgs / f"p{i:04d}.jpg"), quality=90)
+    if not L.read_jpeg(str(imgs / "p0000.jpg").encode()):
+        pytest.skip("libencoder.so was built without stb_image.h")
+    monkeypatch.setenv("M1_MODE", "full")
+    frames = _read_folder(L, imgs, W, H)
+    assert len(frames) == N
+    want = port.encode_stream(frames, 12, 0)
+
+    def run(tag, **env):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        out = tmp_path / tag
+        out.mkdir()
+        rc = host.mpeg_encode_procedure(str(imgs), str(out), str(out / "v.mpeg"), 12)
+        for k in env:
+            monkeypatch.delenv(k)
+        return rc, out
+
+    rc, out = run("stream")
+    assert rc == 0 and (out / "v.mpeg").read_bytes() == want
+    for i in (0, 1, 255, 256, 511, 512, N - 1):
+        y, cb, cr = port.rgb_to_ycbcr(frames[i].reshape(-1, 3))
+        assert (out / f"image_{i + 1}.bit").read_bytes() == np.array([W, H], np.int32).tobytes() + y.tobytes() + cb.tobytes() + cr.tobytes()
+    assert len(list(out.glob("image_*.bit"))) == N
+    rc, out1 = run("onethread", M1_DECODE_THREADS="1")
+    assert rc == 0 and (out1 / "v.mpeg").read_bytes() == want
+    rc, out0 = run("legacy", M1_DECODE_THREADS="0")
+    assert rc == 0 and (out0 / "v.mpeg").read_bytes() == want
+    assert (out0 / "image_300.bit").read_bytes() == (out / "image_300.bit").read_bytes()
+    rc, outd = run("devstream", M1_DEVICE_STREAM="1")
+    assert rc == 0 and (outd / "v.mpeg").read_bytes() == want
+
+    # a file stb cannot decode: its header does not parse -> decode-first path, the file is skipped
+    (imgs / "zz_broken.jpg").write_bytes(b"this is not a JPEG")
+    frames2 = _read_folder(L, imgs, W, H)
+    assert len(frames2) == N
+    rc, outb = run("broken")
+    assert rc == 0 and (outb / "v.mpeg").read_bytes() == port.encode_stream(frames2, 12, 0)
+    (imgs / "zz_broken.jpg").unlink()
+
+    # a picture of another size -> -1, and only the pack + system header in the file
+    PIL.fromarray(np.zeros((H + 16, W, 3), np.uint8)).save(str(imgs / "odd.jpg"))
+    rc, outm = run("mismatch")
+    assert rc == -1 and (outm / "v.mpeg").stat().st_size == 27

@@ -1,6 +1,9 @@
 #!/bin/sh
 # round 2, first GPU call: parity suite, bench, content sweep, phase split with the profiling build
 mkdir -p gpurun_out
+# a tiny encode first: stop at once if the kernel faults
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2a_smoke.txt 2>&1 || { tail -5 gpurun_out/r2a_smoke.txt; echo SMOKE_FAILED; exit 1; }
+tail -1 gpurun_out/r2a_smoke.txt
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/r2a_pytest.txt; cat gpurun_out/r2a_pytest.txt
 python bench.py --steps 10 --warmup 3 --no-cpu-baseline 2>gpurun_out/r2a_bench.err | tail -1 > gpurun_out/r2a_bench.json
 python - <<'PY'
