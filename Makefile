@@ -14,6 +14,17 @@ PKG     := ec504_imageencoder_b200
 HOST    := $(PKG)/csrc/host
 OBJDIR  := $(HOST)/_build
 CFLAGS  := -O2 -g -fPIC -Iinclude -ffp-contract=off -Wall -Wno-unused-result -Wno-stringop-overflow
+# make sharedlib SAN=1 -> $(PKG)/libencoder_san.so: the same host C with AddressSanitizer + UBSan
+# (tools/run_host_sanitizers.sh runs the CPU test suite against it)
+ifeq ($(SAN),1)
+CFLAGS  += -O1 -fsanitize=address,undefined -fno-omit-frame-pointer -fno-sanitize-recover=undefined
+OBJDIR  := $(HOST)/_build_san
+LIBENC  := $(PKG)/libencoder_san.so
+SANLINK := -fsanitize=address,undefined
+else
+LIBENC  := $(PKG)/libencoder.so
+SANLINK :=
+endif
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared
 HOSTSRC := m1_bitvector.c m1_stream.c m1_vlc.c m1_blk.c m1_stages.c m1_decode_helpers.c m1_driver.c m1_stb_stub.c
 HOSTOBJ := $(addprefix $(OBJDIR)/,$(HOSTSRC:.c=.o))
@@ -43,10 +54,12 @@ $(warning *** stb_image.h not found at STB_IMAGE_H=$(STB_IMAGE_H): libencoder.so
 $(warning *** mpeg_encode_procedure() will load no picture and return -1; pass STB_IMAGE_H=/path/to/stb_image.h (v2.30, public domain).)
 endif
 
-sharedlib: $(PKG)/libencoder.so
-$(PKG)/libencoder.so: $(HOSTOBJ) $(STBLINK) $(PKG)/libm1cu.so
-	$(CC) -shared -o $@ $(HOSTOBJ) $(STBLINK) -L$(PKG) -lm1cu -Wl,-rpath,'$$ORIGIN' -lm -lpthread
+sharedlib: $(LIBENC)
+$(LIBENC): $(HOSTOBJ) $(STBLINK) $(PKG)/libm1cu.so
+	$(CC) -shared $(SANLINK) -o $@ $(HOSTOBJ) $(STBLINK) -L$(PKG) -lm1cu -Wl,-rpath,'$$ORIGIN' -lm -lpthread
+ifneq ($(SAN),1)
 	ln -sf $(PKG)/libencoder.so libencoder.so
+endif
 
 encoder: main.c $(PKG)/libencoder.so
 	$(CC) $(CFLAGS) -o $@ main.c -L$(PKG) -lencoder -lm1cu -Wl,-rpath,'$$ORIGIN/$(PKG)' -lm

@@ -81,6 +81,14 @@ __device__ __forceinline__ void ycbcr_exact(int r, int g, int b, int &y, int &cb
 {
     ycbcr_from_doubles(u8_to_double(r), u8_to_double(g), u8_to_double(b), y, cb, cr);
 }
+// byte B of w as a double: one I2F.F64.U8 with a byte selector (XU pipe), no extraction ALU op
+__device__ __forceinline__ double byte_to_double(uint32_t w, int b)   // b is a constant after unrolling
+{
+    double d;
+    const uint32_t s = w >> (8 * b);
+    asm("cvt.rn.f64.u8 %0, %1;" : "=d"(d) : "r"(s));
+    return d;
+}
 #endif
 // host restatement for the test harness (tests/host/block_host.cu): the same chain in plain doubles,
 // every intermediate forced through memory so that no FMA contraction or excess precision can occur

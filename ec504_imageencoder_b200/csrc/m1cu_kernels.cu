@@ -110,6 +110,19 @@ __device__ __forceinline__ HalfTilePixels<CH> load_half_tile(const uint8_t *__re
     return px;
 }
 
+// Which pixels of a half-tile take which arithmetic (compile time; every setting is bit-exact):
+//   2 (product): every pixel by the reference's double chain -- FP64 + conversion pipes, content independent.
+//   0: every pixel by the integer path of m1cu_colour.cuh (IDP.2A / IMAD.WIDE on the FMA pipe, 18 instead of 28
+//      issue slots per pixel), flagged 2x2 quads queued and recomputed exactly after the colour barrier.
+//   1: row 0 integer, row 1 double chain (both pipe groups busy, half the flags).
+// Measured on a B200 (profiles/r2_colour_variants.txt, 1080p x 300, k_encode_chunks ms): 2: 1.37, 0: 1.41, 1: 1.44
+// on the default content; 0 doubles to 2.75 ms on grey or r == g pictures (every quad flagged).  The kernel is bound
+// by latency at 7 resident CTAs per SM, not by the colour arithmetic, so the shorter
+// instruction stream buys nothing and its fix-up pass costs; 0 and 1 are kept for tools/build_experiments.sh
+// and tests/test_gpu_variants.py only.
+#ifndef M1_COLOUR_SPLIT
+#define M1_COLOUR_SPLIT 2
+#endif
 template <int CH>
 __device__ __forceinline__ uint32_t convert_half_tile(const HalfTilePixels<CH> px, int bc, int qy, int C, int *__restrict__ planes)
 {
@@ -124,15 +137,24 @@ __device__ __forceinline__ uint32_t convert_half_tile(const HalfTilePixels<CH> p
     for (int dy = 0; dy < 2; ++dy) {
 #pragma unroll
         for (int j = 0; j < 2; ++j) {                 // 4-pixel groups = 16-byte chunks
-            int yv[4];
+            int yv[4], cbv[4], crv[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int i = 4 * j + e;              // pixel 0..7 of the row
                 const int byte0 = CH * i, wi = byte0 >> 2, sh = byte0 & 3;
-                int cb, cr;
-                colour_int_pixel(w[dy][wi], w[dy][wi + 1 < 2 * CH ? wi + 1 : wi], sh, yv[e], cb, cr, fmin[i >> 1]);
-                if (dy == 0 && (e & 1) == 0) { sb[i >> 1] = cb; sr[i >> 1] = cr; }
-                else                         { sb[i >> 1] += cb; sr[i >> 1] += cr; }
+                int &cb = cbv[e], &cr = crv[e];
+                if (M1_COLOUR_SPLIT == 2 || (M1_COLOUR_SPLIT == 1 && dy == 1))
+                    ycbcr_from_doubles(byte_to_double(w[dy][byte0 >> 2], byte0 & 3), byte_to_double(w[dy][(byte0 + 1) >> 2], (byte0 + 1) & 3),
+                                       byte_to_double(w[dy][(byte0 + 2) >> 2], (byte0 + 2) & 3), yv[e], cb, cr);
+                else
+                    colour_int_pixel(w[dy][wi], w[dy][wi + 1 < 2 * CH ? wi + 1 : wi], sh, yv[e], cb, cr, fmin[i >> 1]);
+            }
+            // 2x2 chroma sums as three-input adds (ALU pipe; the FMA pipe is the integer path's bottleneck)
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                const int q = 2 * j + h2;
+                if (dy == 0) { sb[q] = cbv[2 * h2] + cbv[2 * h2 + 1]; sr[q] = crv[2 * h2] + crv[2 * h2 + 1]; }
+                else         { sb[q] = m1_add3(sb[q], cbv[2 * h2], cbv[2 * h2 + 1]); sr[q] = m1_add3(sr[q], crv[2 * h2], crv[2 * h2 + 1]); }
             }
             *(int4 *)(planes + (a1 ^ ((2 * dy + j) << 2))) = make_int4(yv[0], yv[1], yv[2], yv[3]);
         }
@@ -189,6 +211,13 @@ __device__ __noinline__ void color_half_tile_generic(const uint8_t *__restrict__
 // -------------------------------------------------------------------------------------------
 // kLoad: 3 / 4 = FULL mode with aligned 3- / 4-byte pixels (fast half-tiles), 0 = FULL mode generic
 // loads only, -1 = REF_COMPAT.  One instantiation per input format keeps each kernel's code small.
+// Timing experiment only (tools/, garbage output): M1X_NO_BARRIER replaces the CTA barriers of k_encode_chunks by warp
+// barriers to measure what the barrier waits cost.
+#if defined(M1_EXPERIMENTS) && defined(M1X_NO_BARRIER)
+#define M1_ENC_BARRIER() __syncwarp()
+#else
+#define M1_ENC_BARRIER() __syncthreads()
+#endif
 #ifndef M1_ENC_MIN_CTAS
 #define M1_ENC_MIN_CTAS 7   // 72 registers: 7 CTAs/SM measured best (6: -1.3 %, 8: -4 %, spills)
 #endif
@@ -296,8 +325,8 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
             planes[plane_word(5 * C + mb, r, c, C)] = cr;
         }
     }
-    __syncthreads();
-    if (kLoad > 0) {
+    M1_ENC_BARRIER();
+    if (M1_COLOUR_SPLIT != 2 && kLoad > 0) {
         // Fix-up pass of the integer colour path: the queued quads again, by the reference's double chain
         // (their pixels are L1/L2 hits).  One quad per thread, so the cost follows the NUMBER of flagged
         // quads (about 2 % of them on noise; r == g or g == b pixels are the common causes), not the number of
@@ -314,7 +343,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                 const int q4 = (int)(((unsigned)st * inv) >> 16), bc = st - q4 * nbc;
                 color_quad_exact(fr, g, 16 * mb0 + 8 * bc, 16 * slice + 4 * q4 + 2 * h, bc, 2 * q4 + h, q, C, planes);
             }
-            __syncthreads();
+            M1_ENC_BARRIER();
         }
     }
     win[tid] = 0;                                           // the queue is consumed: `win` becomes the bit window
@@ -370,7 +399,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         if (lane >= d) incl += t;
     }
     if (lane == 31) wtot[warp] = incl;
-    __syncthreads();
+    M1_ENC_BARRIER();
 
     if (kLevels) {
         // debug output: quantised zigzag levels in coding order, [picture][macroblock][6][64]
@@ -384,7 +413,11 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
 
     const int hdr_bits = chunk == 0 ? M1_SLICE_HDR_BITS : 0;
     const int4 wt = *(const int4 *)wtot;                    // blockDim.x <= 128: at most four warps
+#if defined(M1_EXPERIMENTS) && defined(M1X_NO_BARRIER)
+    const int total_bits = min(hdr_bits + wt.x + wt.y + wt.z + wt.w, 8192) & 0x3fff;   // racy garbage stays bounded
+#else
     const int total_bits = hdr_bits + wt.x + wt.y + wt.z + wt.w;
+#endif
     const int base = hdr_bits + (warp > 0 ? wt.x : 0) + (warp > 1 ? wt.y : 0) + (warp > 2 ? wt.z : 0);
     const int my_off = base + incl - my_bits;
 
@@ -394,7 +427,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     if (min(WW, (total_bits + 31) >> 5) + 2 > nthr) {       // uniform; rare at typical qualities
 #pragma unroll 1
         for (int i = nthr + tid; i < WW + 2; i += nthr) win[i] = 0;
-        __syncthreads();
+        M1_ENC_BARRIER();
     }
     for (int w0 = 0;; w0 += 32 * WW) {            // the window words in use are zero here
         if (tid == 0 && hdr_bits && w0 == 0) {
@@ -418,15 +451,15 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                 code_block(ww, rec, pb, nz, is_luma, tb, tid & 7);
             }
         }
-        __syncthreads();
+        M1_ENC_BARRIER();
         const int nwords = min(WW, (total_bits - w0 + 31) >> 5);
 #pragma unroll 1
         for (int i = tid; i < nwords; i += nthr) out[(w0 >> 5) + i] = win[i];
         if (w0 + 32 * WW >= total_bits) break;
-        __syncthreads();                                    // rare: the chunk needs another window pass
+        M1_ENC_BARRIER();                                    // rare: the chunk needs another window pass
 #pragma unroll 1
         for (int i = tid; i < WW + 2; i += nthr) win[i] = 0;
-        __syncthreads();
+        M1_ENC_BARRIER();
     }
     if (tid == 0)
         chunk_bits[(size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk] = (uint32_t)total_bits;

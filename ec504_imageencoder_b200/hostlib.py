@@ -28,9 +28,10 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     _native.m1cu()                                   # libencoder.so links against libm1cu.so
-    if not os.path.exists(_native.LIB_ENCODER):
-        raise RuntimeError(f"{_native.LIB_ENCODER} is missing: run `make sharedlib`")
-    L = C.CDLL(_native.LIB_ENCODER)
+    path = os.environ.get("M1_HOSTLIB") or _native.LIB_ENCODER      # M1_HOSTLIB: the sanitizer build (tools/run_host_sanitizers.sh)
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `make sharedlib`")
+    L = C.CDLL(path)
     bvp, u8p, ip = C.POINTER(BitVector), C.c_void_p, C.c_void_p
     sig = {
         "mpeg_encode_procedure": (C.c_int, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]),

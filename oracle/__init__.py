@@ -93,7 +93,7 @@ class Port(_Base):
     prefix = "m1o_"
 
     def __init__(self):
-        path = os.path.join(HERE, "libm1oracle.so")
+        path = os.environ.get("M1_ORACLE_LIB") or os.path.join(HERE, "libm1oracle.so")   # M1_ORACLE_LIB: sanitizer build
         if not os.path.exists(path):
             build(ref=False)
         super().__init__(path)

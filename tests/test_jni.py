@@ -65,7 +65,8 @@ def test_jni_call_equals_direct_call(jni, tmp_path):
     z = np.load(os.path.join(HERE, "golden", "refcompat_inputs.npz"))
     imgs = tmp_path / "images"
     imgs.mkdir()
-    for i, im in enumerate(z["images"][:6]):                         # the reference fixture's pictures (400 x 144 crop)
+    pics = z["images"][:6]
+    for i, im in enumerate(pics):                                    # the reference fixture's pictures (400 x 144 crop)
         full = np.zeros((600, 400, 3), np.uint8)
         full[:144] = im
         PIL.fromarray(full).save(str(imgs / f"f{i}.jpg"), quality=95)
@@ -74,6 +75,6 @@ def test_jni_call_equals_direct_call(jni, tmp_path):
     rc, c = _call(jni, imgs, tmp_path / "j", tmp_path / "j.mpeg", 12)
     assert rc == 0 and c == [1, 1, 1, 1, 1, 1, 0, 0]
     assert (tmp_path / "j.mpeg").read_bytes() == (tmp_path / "d.mpeg").read_bytes()
-    assert len((tmp_path / "j.mpeg").read_bytes()) > 27 + 6 * 48
-    for i in range(1, 7):
+    assert len((tmp_path / "j.mpeg").read_bytes()) > 27 + len(pics) * 48
+    for i in range(1, len(pics) + 1):
         assert (tmp_path / "j" / f"image_{i}.bit").read_bytes() == (tmp_path / "d" / f"image_{i}.bit").read_bytes()
