@@ -8,7 +8,7 @@
 Workloads (BASELINE.json `configs`):
   N = 1   configs[1]: 300 synthetic 1920x1080 frames, quality 12, resident in HBM; one step = one pass.
           `other_configs` adds configs[0] (SIF x 30), configs[2] (4K x 300 at quality 5 / 12 / 50), one
-          GPU's share of configs[4] (8K x 15) and the content worst cases of the integer colour path.
+          GPU's share of configs[4] (8K x 15) and the content worst cases (noise at quality 50, grey, r == g).
   N > 1   configs[3]: 8000 frames of 1920x1080 split into contiguous frame ranges (rank k encodes
           frame_range(k, N, 8000)); one step = one pass over all 8000 frames INCLUDING the hand-over of every
           rank's compressed segments and per-frame sizes to rank 0 (`scaling: "strong"`).  `weak` repeats the
@@ -447,8 +447,35 @@ class Bench:
         h2d_s = time.perf_counter() - t1
         del dcopy
         d2h = sum(len(p) for p in payloads) + 4 * n + 8 * (n + 1)
-        e2e_s, h2d_s = self.max_over_ranks(e2e_s, h2d_s)
-        return e2e_s, h2d_s, d2h, e2e_steps, host_rgb.numel()
+        nbytes = host_rgb.numel()
+        # the same two measurements with the input in WRITE-COMBINED pinned memory (m1cu_pinned_alloc_wc)
+        wc_e2e_s = wc_h2d_s = float("nan")
+        import ctypes as C
+        lib = enc.lib
+        wc = lib.m1cu_pinned_alloc_wc(nbytes)
+        if wc:
+            try:
+                lib.m1cu_memcpy_d2h(wc, rgb.data_ptr(), nbytes)                      # filled by DMA writes only
+                view = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(wc)).reshape(n, H, W, 3)
+                dst = torch.empty_like(rgb[:n])
+                lib.m1cu_memcpy_h2d(dst.data_ptr(), wc, nbytes)
+                self.fence()
+                t2 = time.perf_counter()
+                lib.m1cu_memcpy_h2d(dst.data_ptr(), wc, nbytes)
+                wc_h2d_s = time.perf_counter() - t2
+                del dst
+                enc.encode_host(view, out=out_np, copy=False)
+                self.fence()
+                t3 = time.perf_counter()
+                for _ in range(e2e_steps):
+                    enc.encode_host(view, out=out_np, copy=False)
+                self.fence()
+                wc_e2e_s = (time.perf_counter() - t3) / e2e_steps
+                del view
+            finally:
+                lib.m1cu_pinned_free(wc)
+        e2e_s, h2d_s, wc_e2e_s, wc_h2d_s = self.max_over_ranks(e2e_s, h2d_s, wc_e2e_s, wc_h2d_s)
+        return e2e_s, h2d_s, d2h, e2e_steps, nbytes, wc_e2e_s, wc_h2d_s
 
 
 def run_ours(args):
@@ -466,7 +493,7 @@ def run_ours(args):
 
     # e2e on a bounded sample of the same frames (300 per rank: 1.87 GB of pinned host memory per rank)
     n_e2e = min(n_local, FRAMES_PER_STEP)
-    e2e_s, h2d_s, d2h, e2e_steps, h2d_bytes = b.e2e(head["enc"], head["rgb"], n_e2e)
+    e2e_s, h2d_s, d2h, e2e_steps, h2d_bytes, wc_e2e_s, wc_h2d_s = b.e2e(head["enc"], head["rgb"], n_e2e)
     head.pop("enc").close()
     head.pop("rgb")
     b.torch.cuda.empty_cache()
@@ -482,8 +509,8 @@ def run_ours(args):
                      ("configs[4] 8K, one GPU's share of 120 frames over 8 (15 frames)", 7680, 4320, 15, 12, SYNTH_NATURAL),
                      ("1080p x 300 noise, quality 12", W, H, 300, 12, SYNTH_NOISE),
                      ("1080p x 300 noise, quality 50 (VLC stress)", W, H, 300, 50, SYNTH_NOISE),
-                     ("1080p x 300 grey (every pixel takes the colour fix-up), quality 12", W, H, 300, 12, SYNTH_GREY),
-                     ("1080p x 300 r == g (every pixel takes the colour fix-up), quality 12", W, H, 300, 12, SYNTH_RG_EQUAL)]
+                     ("1080p x 300 grey (every pixel an exact-quotient case of the colour arithmetic), quality 12", W, H, 300, 12, SYNTH_GREY),
+                     ("1080p x 300 r == g (every pixel an exact-quotient case of Cb), quality 12", W, H, 300, 12, SYNTH_RG_EQUAL)]
             for name, w, h, nfr, q, kind in cases:
                 r = b.measure(w, h, nfr, q, kind, osteps, 3, sharded=False, check_frames=1 if w * h > 3000 * 2000 else 2)
                 r.pop("enc").close(); r.pop("rgb")
@@ -532,6 +559,9 @@ def run_ours(args):
                     "plain_h2d_aggregate_gbs": world * h2d_bytes / h2d_s / 1e9,
                     "e2e_input_gbs": world * h2d_bytes / e2e_s / 1e9,
                     "frac_of_plain_h2d": h2d_s / e2e_s,
+                    "write_combined_input": {"value": world * n_e2e / wc_e2e_s, "unit": UNIT,
+                                             "plain_h2d_aggregate_gbs": world * h2d_bytes / wc_h2d_s / 1e9,
+                                             "note": "same call with the input in cudaHostAllocWriteCombined memory (m1cu_pinned_alloc_wc)"},
                     "note": ("bound by the host->device copy of the RGB input: plain_h2d_* is a bare pinned copy of the same bytes "
                              "issued by all ranks at the same time (per rank / summed), e2e_input_gbs the RGB bytes per second the "
                              "whole call sustains, frac_of_plain_h2d their ratio; "
@@ -542,8 +572,9 @@ def run_ours(args):
                          "peak_source": b.peak_src,
                          "algorithmic_bytes_per_frame": head["alg_bytes_per_frame"], "frames_per_launch": head["frames_per_launch"],
                          "launch_ms": head["launch_ms"], "whole_step_frac": head["whole_step_frac"],
-                         "note": ("the dominant kernel is instruction-issue bound, not HBM bound (DESIGN.md section 7): integer colour "
-                                  "path + int32 DCT + VLC cost about 50 issue slots per pixel"),
+                         "note": ("the dominant kernel is not HBM bound: 7 resident CTAs per SM cannot hide its own latency (ms per pass = "
+                                  "0.81 + 3.95 / resident CTAs, profiles/r2_occupancy.txt) and the exact double-precision colour "
+                                  "chain + int32 DCT + VLC cost about 60 issue slots per pixel (DESIGN.md section 7)"),
                          "kernel_ms_per_step": head["kernel_ms_per_step"]},
         }
         if head["gather"] is not None:

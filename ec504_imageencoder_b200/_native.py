@@ -67,10 +67,11 @@ def m1cu() -> C.CDLL:
     global _m1cu
     if _m1cu is not None:
         return _m1cu
-    if not os.path.exists(LIB_M1CU):
-        raise RuntimeError(f"{LIB_M1CU} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    path = os.environ.get("M1CU_LIB") or LIB_M1CU       # M1CU_LIB: a tools/build_experiments.sh variant (tests only)
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                            "(there is no CPU fallback for the encode path)")
-    lib = C.CDLL(LIB_M1CU, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
     vp, u8p, i32p, u32p, u64p, i16p = (C.c_void_p,) * 6
     sig = {
         "m1cu_abi_version": (C.c_int, []),
@@ -99,6 +100,7 @@ def m1cu() -> C.CDLL:
         "m1cu_device_free": (None, [vp]),
         "m1cu_pinned_alloc": (vp, [C.c_size_t]),
         "m1cu_pinned_free": (None, [vp]),
+        "m1cu_pinned_alloc_wc": (vp, [C.c_size_t]),
         "m1cu_memcpy_h2d": (C.c_int, [vp, vp, C.c_size_t]),
         "m1cu_memcpy_d2h": (C.c_int, [vp, vp, C.c_size_t]),
         "m1cu_ipc_export": (C.c_int, [vp, C.c_char_p]),
@@ -122,7 +124,7 @@ M1CU_SYMBOLS = (
     "m1cu_frame_bytes_in", "m1cu_payload_bound", "m1cu_typical_out_bytes", "m1cu_encode_device",
     "m1cu_check", "m1cu_encode_host", "m1cu_ycbcr_planes", "m1cu_host_batch_planes", "m1cu_synth_rgb", "m1cu_launch_count",
     "m1cu_enable_timing", "m1cu_kernel_times",
-    "m1cu_device_alloc", "m1cu_device_free", "m1cu_pinned_alloc", "m1cu_pinned_free",
+    "m1cu_device_alloc", "m1cu_device_free", "m1cu_pinned_alloc", "m1cu_pinned_free", "m1cu_pinned_alloc_wc",
     "m1cu_memcpy_h2d", "m1cu_memcpy_d2h",
     "m1cu_ipc_export", "m1cu_ipc_open", "m1cu_ipc_close", "m1cu_push_payloads", "m1cu_assemble_stream",
     "m1cu_encode_host_stream",

@@ -632,6 +632,9 @@ void *m1cu_device_alloc(size_t bytes) { void *p = nullptr; if (cudaMalloc(&p, by
 void  m1cu_device_free(void *p) { if (p) cudaFree(p); }
 void *m1cu_pinned_alloc(size_t bytes) { void *p = nullptr; if (cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 void  m1cu_pinned_free(void *p) { if (p) cudaFreeHost(p); }
+// write-combined pinned memory: the CPU must only WRITE it (reads are uncached and very slow); DMA reads skip the
+// cache snoop, which can raise host->device throughput when several GPUs pull from one host memory system
+void *m1cu_pinned_alloc_wc(size_t bytes) { void *p = nullptr; if (cudaHostAlloc(&p, bytes, cudaHostAllocWriteCombined) != cudaSuccess) { cudaGetLastError(); return nullptr; } return p; }
 // A pageable source is only staged when cudaMemcpy returns; the wait on the legacy stream makes the
 // bytes visible to work submitted afterwards on the contexts' non-blocking streams.
 int   m1cu_memcpy_h2d(void *dst, const void *src, size_t bytes)

@@ -154,6 +154,7 @@ void *m1cu_device_alloc(size_t bytes);
 void  m1cu_device_free(void *p);
 void *m1cu_pinned_alloc(size_t bytes);
 void  m1cu_pinned_free(void *p);
+void *m1cu_pinned_alloc_wc(size_t bytes);  /* write-combined pinned memory (fill it with writes only); free with m1cu_pinned_free */
 int   m1cu_memcpy_h2d(void *dst, const void *src, size_t bytes);
 int   m1cu_memcpy_d2h(void *dst, const void *src, size_t bytes);
 

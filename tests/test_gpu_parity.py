@@ -108,10 +108,11 @@ def test_color_all_2_24(m1, port):
 
 
 def test_encode_kernel_all_colours_all_alignments(m1, port):
-    """All 2^24 colours through k_encode_chunks' integer colour path + fix-up queue (not through the
-    plane kernel): four 4096x4096 pictures holding every colour once, shifted by 0..3 pixels so that every
-    colour meets each of the four byte alignments of a packed 3-byte pixel.  Quality 89: the finest
-    quantiser the reference can encode keeps single-sample errors visible in the levels."""
+    """All 2^24 colours through k_encode_chunks' colour phase (not through the plane kernel): four
+    4096x4096 pictures holding every colour once, shifted by 0..3 pixels so that every colour meets each of
+    the four byte alignments of a packed 3-byte pixel.  Quality 89: the finest quantiser the reference can
+    encode keeps single-sample errors visible in the levels.  (tests/test_gpu_variants.py repeats it on the
+    integer-colour build.)"""
     g = np.arange(1 << 24, dtype=np.uint32)
     base = np.stack([g >> 16, (g >> 8) & 255, g & 255], axis=1).astype(np.uint8)
     enc = m1.M1Encoder(4096, 4096, 3, MODE_FULL, 89, max_frames=1)
@@ -126,9 +127,10 @@ def test_encode_kernel_all_colours_all_alignments(m1, port):
 
 @pytest.mark.parametrize("kind", [SYNTH_GREY, SYNTH_RG_EQUAL])
 @pytest.mark.parametrize("W,H,q", [(352, 240, 12), (1920, 1080, 50), (100, 70, 89)])
-def test_fixup_queue_worst_cases(m1, port, kind, W, H, q):
-    """Grey and r == g pictures: every 2x2 quad of every chunk is queued for the exact recomputation
-    (the queue is exactly as large as a chunk has quads)."""
+def test_exact_quotient_worst_cases(m1, port, kind, W, H, q):
+    """Grey and r == g pictures: every pixel is one of the colours where the reference's double chain can
+    land one ulp below an integer, the worst case for any shortcut in the colour
+    arithmetic (on the integer-colour build every 2x2 quad of every chunk is queued for recomputation)."""
     _encode_both(m1, port, W, H, 2, q, kind)
 
 
