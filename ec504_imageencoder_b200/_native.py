@@ -94,7 +94,6 @@ def m1cu() -> C.CDLL:
         "m1cu_host_batch_planes": (C.c_int, [vp, C.c_int, u8p, C.c_size_t]),
         "m1cu_synth_rgb": (C.c_int, [vp, C.c_uint32, C.c_long, C.c_int, C.c_int, u8p]),
         "m1cu_launch_count": (C.c_ulonglong, [vp]),
-        "m1cu_encode_kernel_name": (C.c_char_p, [vp]),
         "m1cu_enable_timing": (C.c_int, [vp, C.c_int]),
         "m1cu_kernel_times": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
         "m1cu_device_alloc": (vp, [C.c_size_t]),
@@ -124,7 +123,7 @@ M1CU_SYMBOLS = (
     "m1cu_destroy", "m1cu_set_stream", "m1cu_synchronize", "m1cu_macroblocks_per_frame",
     "m1cu_frame_bytes_in", "m1cu_payload_bound", "m1cu_typical_out_bytes", "m1cu_encode_device",
     "m1cu_check", "m1cu_encode_host", "m1cu_ycbcr_planes", "m1cu_host_batch_planes", "m1cu_synth_rgb", "m1cu_launch_count",
-    "m1cu_encode_kernel_name", "m1cu_enable_timing", "m1cu_kernel_times",
+    "m1cu_enable_timing", "m1cu_kernel_times",
     "m1cu_device_alloc", "m1cu_device_free", "m1cu_pinned_alloc", "m1cu_pinned_free", "m1cu_pinned_alloc_wc",
     "m1cu_memcpy_h2d", "m1cu_memcpy_d2h",
     "m1cu_ipc_export", "m1cu_ipc_open", "m1cu_ipc_close", "m1cu_push_payloads", "m1cu_assemble_stream",

@@ -43,7 +43,6 @@ struct m1cu_ctx {
     bool own_stream = false;
     // device state
     uint32_t *d_staging = nullptr, *d_chunk_bits = nullptr, *d_chunk_dst = nullptr;
-    unsigned int *d_redo = nullptr;                            // [0] count, [1..] chunk ids handed back by k_encode_groups
     M1Tables *d_tables = nullptr;
     // m1cu_assemble_stream: prefix templates (256 x 44) + prologue (27) on the device, the host copy they came from
     uint8_t *d_stream_tmpl = nullptr;
@@ -215,7 +214,6 @@ int m1cu_create_ex(m1cu_ctx **out, int device, int width, int height, int channe
 #else
     g.debug_skip = 0;
 #endif
-    g.cta_per_chunk = (tuning && tuning->cta_per_chunk) ? 1 : 0;
     g.win_words = M1_WIN_WORDS;
     if (tuning && tuning->win_words) {                     // tests: force the multi-window path
         if (tuning->win_words < 4 || tuning->win_words > M1_WIN_WORDS) {
@@ -243,7 +241,6 @@ int m1cu_create_ex(m1cu_ctx **out, int device, int width, int height, int channe
     CUC(cudaMalloc(&ctx->d_staging, per_frame * batch));
     CUC(cudaMalloc(&ctx->d_chunk_bits, sizeof(uint32_t) * g.chunks_per_frame * batch));
     CUC(cudaMalloc(&ctx->d_chunk_dst, sizeof(uint32_t) * g.chunks_per_frame * batch));
-    CUC(cudaMalloc(&ctx->d_redo, sizeof(unsigned int) * ((size_t)g.chunks_per_frame * batch + 1)));
     CUC(cudaMalloc(&ctx->d_tables, sizeof(M1Tables)));
     CUC(cudaMalloc(&ctx->d_err, sizeof(int)));
     CUC(cudaMalloc(&ctx->d_running, sizeof(unsigned long long)));
@@ -268,7 +265,7 @@ int m1cu_destroy(m1cu_ctx *ctx)
     if (!ctx) return M1CU_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    cudaFree(ctx->d_staging); cudaFree(ctx->d_chunk_bits); cudaFree(ctx->d_chunk_dst); cudaFree(ctx->d_redo);
+    cudaFree(ctx->d_staging); cudaFree(ctx->d_chunk_bits); cudaFree(ctx->d_chunk_dst);
     cudaFree(ctx->d_tables); cudaFree(ctx->d_stream_tmpl); cudaFree(ctx->d_seg_off); cudaFree(ctx->d_stream); cudaFree(ctx->d_stream_end); cudaFree(ctx->d_err); cudaFree(ctx->d_running); cudaFree(ctx->d_done);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_fbytes); cudaFree(ctx->d_foff);
     cudaFree(ctx->d_levels); cudaFree(ctx->d_planes);
@@ -348,7 +345,7 @@ int m1cu_encode_device(m1cu_ctx *ctx, const uint8_t *d_rgb, int n_frames, uint8_
             Timed t(ctx, 0);
             CU(m1k_launch_encode(g, ctx->q, d_rgb + (size_t)f0 * g.frame_stride, nb, ctx->d_tables, ctx->d_staging,
                                  ctx->d_chunk_bits, d_levels ? d_levels + (size_t)f0 * g.mbs_per_frame * 384 : nullptr,
-                                 ctx->d_err, ctx->d_redo, ctx->d_redo + 1, st));
+                                 ctx->d_err, st));
         }
         {
             Timed t(ctx, 1);
@@ -361,7 +358,7 @@ int m1cu_encode_device(m1cu_ctx *ctx, const uint8_t *d_rgb, int n_frames, uint8_
             CU(m1k_launch_stitch(g, nb, bx, ctx->d_staging, ctx->d_chunk_bits, ctx->d_chunk_dst, d_frame_bytes + f0,
                                  (const unsigned long long *)d_frame_offsets + f0, d_out, (unsigned long long)out_cap, st));
         }
-        ctx->launches += m1k_use_groups(g) ? 4 : 3;
+        ctx->launches += 3;
     }
     return M1CU_OK;
 }
@@ -609,12 +606,6 @@ int m1cu_synth_rgb(m1cu_ctx *ctx, uint32_t seed, long first_frame, int n_frames,
 }
 
 unsigned long long m1cu_launch_count(const m1cu_ctx *ctx) { return ctx ? ctx->launches : 0; }
-
-const char *m1cu_encode_kernel_name(const m1cu_ctx *ctx)
-{
-    if (!ctx) return "";
-    return m1k_use_groups(ctx->g) ? "k_encode_groups (+ k_encode_redo)" : "k_encode_chunks";
-}
 
 int m1cu_enable_timing(m1cu_ctx *ctx, int on)
 {

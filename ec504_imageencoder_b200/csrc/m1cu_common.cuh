@@ -28,8 +28,7 @@ struct M1Geom {
     int mode;                  // M1CU_MODE_*
     int fast_load;             // 3 / 4: channels with 16-byte-aligned 16-pixel tiles, 0: generic loads only
     int win_words;             // bit-window words actually used (= M1_WIN_WORDS; tests shrink it via M1_WIN_WORDS)
-    int debug_skip;            // profiling build only (M1_DEBUG_SKIP): bit 0 skips the colour phase, bit 1 the block phases
-    int cta_per_chunk;         // m1cu_tuning: 1 = never use the warp-per-chunk kernel (k_encode_groups)
+    int debug_skip;            // profiling only (env M1_DEBUG_SKIP): bit 0 skips the colour phase, bit 1 the block phases
     int slices;                // per picture
     int mbs_per_slice;
     int chunk_mbs;             // macroblocks per chunk (last chunk of a slice may hold fewer)

@@ -211,17 +211,26 @@ __device__ __noinline__ void color_half_tile_generic(const uint8_t *__restrict__
 // -------------------------------------------------------------------------------------------
 // kLoad: 3 / 4 = FULL mode with aligned 3- / 4-byte pixels (fast half-tiles), 0 = FULL mode generic
 // loads only, -1 = REF_COMPAT.  One instantiation per input format keeps each kernel's code small.
+// Timing experiment only (tools/, garbage output): M1X_NO_BARRIER replaces the CTA barriers of k_encode_chunks by warp
+// barriers to measure what the barrier waits cost.
+#if defined(M1_EXPERIMENTS) && defined(M1X_NO_BARRIER)
+#define M1_ENC_BARRIER() __syncwarp()
+#else
+#define M1_ENC_BARRIER() __syncthreads()
+#endif
 #ifndef M1_ENC_MIN_CTAS
 #define M1_ENC_MIN_CTAS 7   // 72 registers: 7 CTAs/SM measured best (6: -1.3 %, 8: -4 %, spills)
 #endif
 template <int kLoad, bool kLevels>
-__device__ __forceinline__ void
-encode_chunk_cta(const M1Geom &g, const M1NzKeys &nk, const uint8_t *__restrict__ rgb, const M1Tables *__restrict__ gtab,
-                 uint32_t *__restrict__ staging, uint32_t *__restrict__ chunk_bits, short *__restrict__ levels,
-                 int *__restrict__ err, const int chunk, const int slice, const int frame)
+__global__ void __launch_bounds__(128, M1_ENC_MIN_CTAS)
+k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKeys nk,
+                const uint8_t *__restrict__ rgb, const M1Tables *__restrict__ gtab,
+                uint32_t *__restrict__ staging, uint32_t *__restrict__ chunk_bits,
+                short *__restrict__ levels, int *__restrict__ err)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x, nthr = blockDim.x;
+    const int chunk = blockIdx.x, slice = blockIdx.y, frame = blockIdx.z;
     const int C = g.chunk_mbs;
     const int mb0 = chunk * C;
     const int nmb = min(C, g.mbs_per_slice - mb0);
@@ -316,7 +325,7 @@ encode_chunk_cta(const M1Geom &g, const M1NzKeys &nk, const uint8_t *__restrict_
             planes[plane_word(5 * C + mb, r, c, C)] = cr;
         }
     }
-    __syncthreads();
+    M1_ENC_BARRIER();
     if (M1_COLOUR_SPLIT != 2 && kLoad > 0) {
         // Fix-up pass of the integer colour path: the queued quads again, by the reference's double chain
         // (their pixels are L1/L2 hits).  One quad per thread, so the cost follows the NUMBER of flagged
@@ -334,7 +343,7 @@ encode_chunk_cta(const M1Geom &g, const M1NzKeys &nk, const uint8_t *__restrict_
                 const int q4 = (int)(((unsigned)st * inv) >> 16), bc = st - q4 * nbc;
                 color_quad_exact(fr, g, 16 * mb0 + 8 * bc, 16 * slice + 4 * q4 + 2 * h, bc, 2 * q4 + h, q, C, planes);
             }
-            __syncthreads();
+            M1_ENC_BARRIER();
         }
     }
     win[tid] = 0;                                           // the queue is consumed: `win` becomes the bit window
@@ -390,7 +399,7 @@ encode_chunk_cta(const M1Geom &g, const M1NzKeys &nk, const uint8_t *__restrict_
         if (lane >= d) incl += t;
     }
     if (lane == 31) wtot[warp] = incl;
-    __syncthreads();
+    M1_ENC_BARRIER();
 
     if (kLevels) {
         // debug output: quantised zigzag levels in coding order, [picture][macroblock][6][64]
@@ -404,7 +413,11 @@ encode_chunk_cta(const M1Geom &g, const M1NzKeys &nk, const uint8_t *__restrict_
 
     const int hdr_bits = chunk == 0 ? M1_SLICE_HDR_BITS : 0;
     const int4 wt = *(const int4 *)wtot;                    // blockDim.x <= 128: at most four warps
+#if defined(M1_EXPERIMENTS) && defined(M1X_NO_BARRIER)
+    const int total_bits = min(hdr_bits + wt.x + wt.y + wt.z + wt.w, 8192) & 0x3fff;   // racy garbage stays bounded
+#else
     const int total_bits = hdr_bits + wt.x + wt.y + wt.z + wt.w;
+#endif
     const int base = hdr_bits + (warp > 0 ? wt.x : 0) + (warp > 1 ? wt.y : 0) + (warp > 2 ? wt.z : 0);
     const int my_off = base + incl - my_bits;
 
@@ -414,7 +427,7 @@ encode_chunk_cta(const M1Geom &g, const M1NzKeys &nk, const uint8_t *__restrict_
     if (min(WW, (total_bits + 31) >> 5) + 2 > nthr) {       // uniform; rare at typical qualities
 #pragma unroll 1
         for (int i = nthr + tid; i < WW + 2; i += nthr) win[i] = 0;
-        __syncthreads();
+        M1_ENC_BARRIER();
     }
     for (int w0 = 0;; w0 += 32 * WW) {            // the window words in use are zero here
         if (tid == 0 && hdr_bits && w0 == 0) {
@@ -438,52 +451,19 @@ encode_chunk_cta(const M1Geom &g, const M1NzKeys &nk, const uint8_t *__restrict_
                 code_block(ww, rec, pb, nz, is_luma, tb, tid & 7);
             }
         }
-        __syncthreads();
+        M1_ENC_BARRIER();
         const int nwords = min(WW, (total_bits - w0 + 31) >> 5);
 #pragma unroll 1
         for (int i = tid; i < nwords; i += nthr) out[(w0 >> 5) + i] = win[i];
         if (w0 + 32 * WW >= total_bits) break;
-        __syncthreads();                                    // rare: the chunk needs another window pass
+        M1_ENC_BARRIER();                                    // rare: the chunk needs another window pass
 #pragma unroll 1
         for (int i = tid; i < WW + 2; i += nthr) win[i] = 0;
-        __syncthreads();
+        M1_ENC_BARRIER();
     }
     if (tid == 0)
         chunk_bits[(size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk] = (uint32_t)total_bits;
 }
-
-template <int kLoad, bool kLevels>
-__global__ void __launch_bounds__(128, M1_ENC_MIN_CTAS)
-k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKeys nk,
-                const uint8_t *__restrict__ rgb, const M1Tables *__restrict__ gtab,
-                uint32_t *__restrict__ staging, uint32_t *__restrict__ chunk_bits,
-                short *__restrict__ levels, int *__restrict__ err)
-{
-    encode_chunk_cta<kLoad, kLevels>(g, nk, rgb, gtab, staging, chunk_bits, levels, err, blockIdx.x, blockIdx.y, blockIdx.z);
-}
-
-// The same CTA-per-chunk encoder over a LIST of chunks: the chunks k_encode_groups handed back (a block
-// longer than 64 bits, or more bits than its per-warp window holds).  A few persistent CTAs; the list is
-// usually empty.  Entry = frame * chunks_per_frame + slice * chunks_per_slice + chunk.
-template <int kLoad, bool kLevels>
-__global__ void __launch_bounds__(128, M1_ENC_MIN_CTAS)
-k_encode_redo(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKeys nk,
-              const uint8_t *__restrict__ rgb, const M1Tables *__restrict__ gtab,
-              uint32_t *__restrict__ staging, uint32_t *__restrict__ chunk_bits,
-              short *__restrict__ levels, int *__restrict__ err,
-              const unsigned int *__restrict__ redo_count, const unsigned int *__restrict__ redo_list)
-{
-    const unsigned int n = *redo_count;
-    for (unsigned int i = blockIdx.x; i < n; i += gridDim.x) {
-        const unsigned int id = redo_list[i];
-        const int frame = (int)(id / (unsigned)g.chunks_per_frame), r = (int)(id % (unsigned)g.chunks_per_frame);
-        encode_chunk_cta<kLoad, kLevels>(g, nk, rgb, gtab, staging, chunk_bits, levels, err, r % g.chunks_per_slice,
-                                         r / g.chunks_per_slice, frame);
-        __syncthreads();                                    // shared memory is reused by the next entry
-    }
-}
-
-#include "m1cu_encode_groups.cuh"
 
 // -------------------------------------------------------------------------------------------
 // k_layout: one CTA per picture.  Slice s starts at a byte boundary (include/encoder.h:442-443);
@@ -801,30 +781,6 @@ static encode_kernel_t pick_encode_kernel(const M1Geom &g, bool levels)
     return levels ? k_encode_chunks<0, true> : k_encode_chunks<0, false>;
 }
 
-typedef void (*groups_kernel_t)(const M1Geom, const M1NzKeys, const uint8_t *, const M1Tables *, int, uint32_t *, uint32_t *,
-                                short *, int *, unsigned int *, unsigned int *);
-typedef void (*redo_kernel_t)(const M1Geom, const M1NzKeys, const uint8_t *, const M1Tables *, uint32_t *, uint32_t *,
-                              short *, int *, const unsigned int *, const unsigned int *);
-
-// k_encode_groups applies to FULL mode with aligned 3- / 4-byte pixels (g.fast_load, cleared by the caller for an
-// unaligned input pointer) unless the context was created with m1cu_tuning.cta_per_chunk.
-bool m1k_use_groups(const M1Geom &g) { return g.mode == 0 && (g.fast_load == 3 || g.fast_load == 4) && !g.cta_per_chunk; }
-
-static groups_kernel_t pick_groups_kernel(const M1Geom &g, bool levels)
-{
-    if (g.fast_load == 4) return levels ? k_encode_groups<4, true> : k_encode_groups<4, false>;
-    return levels ? k_encode_groups<3, true> : k_encode_groups<3, false>;
-}
-static redo_kernel_t pick_redo_kernel(const M1Geom &g, bool levels)
-{
-    if (g.fast_load == 4) return levels ? k_encode_redo<4, true> : k_encode_redo<4, false>;
-    return levels ? k_encode_redo<3, true> : k_encode_redo<3, false>;
-}
-static size_t groups_smem_bytes()
-{
-    return (size_t)M1G_WARPS * M1G_WARP_WORDS * 4 + (((size_t)offsetof(M1Tables, ka) + 15) / 16) * 16;
-}
-
 cudaError_t m1k_prepare(const M1Geom &g)
 {
     const size_t smem = m1k_encode_smem_bytes(g, m1k_encode_threads(g));
@@ -837,42 +793,18 @@ cudaError_t m1k_prepare(const M1Geom &g)
             if (e != cudaSuccess) return e;
         }
     }
-    if (g.mode == 0 && (g.fast_load == 3 || g.fast_load == 4)) {
-        for (bool lv : { false, true }) {
-            cudaError_t e = cudaFuncSetAttribute(pick_groups_kernel(g, lv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)groups_smem_bytes());
-            if (e != cudaSuccess) return e;
-            e = cudaFuncSetAttribute(pick_redo_kernel(g, lv), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-        }
-    }
     return cudaSuccess;
 }
 
 cudaError_t m1k_launch_encode(const M1Geom &g, const M1Quant &q, const uint8_t *rgb, int n_frames,
                               const M1Tables *tables, uint32_t *staging, uint32_t *chunk_bits,
-                              short *levels, int *err, unsigned int *redo_count, unsigned int *redo_list, cudaStream_t st)
+                              short *levels, int *err, cudaStream_t st)
 {
     const int threads = m1k_encode_threads(g);
     const size_t smem = m1k_encode_smem_bytes(g, threads);
+    dim3 grid(g.chunks_per_slice, g.slices, n_frames);
     M1NzKeys nk;
     m1k_nz_keys(q, &nk);
-    if (m1k_use_groups(g) && redo_count && redo_list) {
-        // warp-per-chunk kernel, then the (usually empty) list of chunks it handed back, CTA per chunk
-        const int n_groups = g.chunks_per_frame * n_frames;
-        cudaError_t e = cudaMemsetAsync(redo_count, 0, sizeof(unsigned int), st);
-        if (e != cudaSuccess) return e;
-        pick_groups_kernel(g, levels != nullptr)<<<(n_groups + M1G_WARPS - 1) / M1G_WARPS, 32 * M1G_WARPS, groups_smem_bytes(), st>>>(
-            g, nk, rgb, tables, n_groups, staging, chunk_bits, levels, err, redo_count, redo_list);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        int dev = 0, sms = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        pick_redo_kernel(g, levels != nullptr)<<<2 * sms, threads, smem, st>>>(g, nk, rgb, tables, staging, chunk_bits, levels, err,
-                                                                               redo_count, redo_list);
-        return cudaGetLastError();
-    }
-    dim3 grid(g.chunks_per_slice, g.slices, n_frames);
     pick_encode_kernel(g, levels != nullptr)<<<grid, threads, smem, st>>>(g, nk, rgb, tables, staging, chunk_bits, levels, err);
     return cudaGetLastError();
 }

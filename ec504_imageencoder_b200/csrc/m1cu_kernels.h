@@ -7,11 +7,9 @@ int         m1k_encode_threads(const M1Geom &g);
 cudaError_t m1k_prepare(const M1Geom &g);
 // (m1k_fill_tables / m1_make_quant: inline in m1cu_quant.h)
 
-bool        m1k_use_groups(const M1Geom &g);
-// redo_count / redo_list (1 / chunks_per_frame * n_frames words): scratch of the warp-per-chunk kernel
 cudaError_t m1k_launch_encode(const M1Geom &g, const M1Quant &q, const uint8_t *rgb, int n_frames,
                               const M1Tables *tables, uint32_t *staging, uint32_t *chunk_bits,
-                              short *levels, int *err, unsigned int *redo_count, unsigned int *redo_list, cudaStream_t st);
+                              short *levels, int *err, cudaStream_t st);
 cudaError_t m1k_launch_layout(const M1Geom &g, int n_frames, const uint32_t *chunk_bits, uint32_t *chunk_dst,
                               uint32_t *frame_bytes, unsigned long long *frame_off,
                               unsigned long long *running, unsigned int *done_counter,

@@ -83,8 +83,6 @@ typedef struct m1cu_tuning {
     int chunk_mbs;   /* macroblocks per CTA, 1..16 (default 16: full chunks + one shorter tail per slice) */
     int chunk_even;  /* != 0: equal chunks per slice instead                                            */
     int win_words;   /* shared-memory bit-window words per pass, 4..512 (default 512)                   */
-    int cta_per_chunk; /* != 0: always the CTA-per-chunk kernel (k_encode_chunks), never the warp-per-chunk
-                          kernel (k_encode_groups) that FULL mode with aligned 3- / 4-byte pixels uses      */
 } m1cu_tuning;
 int  m1cu_create_ex(m1cu_ctx **out, int device, int width, int height, int channels,
                     int mode, int quality_factor, int max_frames, const m1cu_tuning *tuning);
@@ -143,14 +141,10 @@ int m1cu_synth_rgb(m1cu_ctx *ctx, uint32_t seed, long first_frame, int n_frames,
 /* counters: kernels launched by this context since creation (for bench.py's gpu_launches) */
 unsigned long long m1cu_launch_count(const m1cu_ctx *ctx);
 
-/* Which encode kernel this context launches for 16-byte-aligned input: "k_encode_groups (+ k_encode_redo)" (warp per
- * chunk; FULL mode, 3- / 4-byte pixels, width a multiple of 16) or "k_encode_chunks" (CTA per chunk; everything else). */
-const char *m1cu_encode_kernel_name(const m1cu_ctx *ctx);
-
 /* Per-kernel device timing for the roofline report.  While enabled, every launch of the three
  * pipeline kernels is bracketed by CUDA events on the context's stream.  m1cu_kernel_times
  * synchronises, adds the elapsed milliseconds of all launches recorded since the last call into
- * ms[0..2] (0 = the encode kernel(s), see m1cu_encode_kernel_name, 1 = k_layout, 2 = k_stitch) and their counts into n[0..2],
+ * ms[0..2] (0 = k_encode_chunks, 1 = k_layout, 2 = k_stitch) and their counts into n[0..2],
  * then forgets them. */
 int m1cu_enable_timing(m1cu_ctx *ctx, int on);
 int m1cu_kernel_times(m1cu_ctx *ctx, double ms[3], unsigned long long n[3]);

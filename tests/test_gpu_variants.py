@@ -17,10 +17,7 @@ CASES = ((352, 240, 3, 12, 0), (1920, 1080, 2, 12, 0), (640, 480, 2, 50, 1), (19
 
 
 @pytest.mark.parametrize("tuning", [{"chunk_mbs": 7}, {"chunk_mbs": 1}, {"chunk_mbs": 11}, {"chunk_even": True},
-                                    {"cta_per_chunk": True}, {"cta_per_chunk": True, "chunk_mbs": 7},
-                                    {"cta_per_chunk": True, "chunk_mbs": 1}, {"cta_per_chunk": True, "chunk_even": True},
-                                    {"win_words": 8}, {"win_words": 5, "chunk_mbs": 3}, {"win_words": 6, "chunk_mbs": 5},
-                                    {"cta_per_chunk": True, "win_words": 8}, {"cta_per_chunk": True, "win_words": 5, "chunk_mbs": 3}])
+                                    {"win_words": 8}, {"win_words": 5, "chunk_mbs": 3}, {"win_words": 6, "chunk_mbs": 5}])
 def test_kernel_variant(tuning, port):
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
@@ -36,39 +33,6 @@ def test_kernel_variant(tuning, port):
             assert np.array_equal(lev[f], rl), (W, H, f)
             assert pay[f] == rp and pay2[f] == rp, (W, H, f)
         enc.close()
-
-
-def test_both_encode_kernels_and_the_redo_list(port):
-    """FULL mode with aligned pixels runs k_encode_groups (a warp per chunk); chunks with a block longer than 64
-    bits or more bits than the warp's window go through k_encode_redo (the CTA-per-chunk encoder over a list).
-    Noise at quality 89 makes most blocks long; both kernels and the mixture must give the oracle's bytes."""
-    if not torch.cuda.is_available():
-        pytest.skip("no GPU")
-    from ec504_imageencoder_b200 import M1Encoder
-    for (W, H, n, q, kind) in ((1920, 1080, 2, 89, 1), (352, 240, 3, 89, 1), (1920, 1088, 1, 75, 1), (64, 48, 2, 89, 1),
-                               (3840, 2160, 1, 50, 1), (352, 240, 2, 1, 0)):
-        want = None
-        for legacy in (False, True):
-            enc = M1Encoder(W, H, 3, 0, q, max_frames=n, cta_per_chunk=legacy)
-            assert ("k_encode_chunks" in enc.encode_kernel) == legacy
-            rgb = enc.synth_rgb(99, 3, n, kind)
-            res = enc.encode_device(rgb, want_levels=True)
-            pay, lev, host = res.payloads(), res.levels.cpu().numpy(), rgb.cpu().numpy()
-            if want is None:
-                want = [port.encode_picture(host[f], q, 0, want_levels=True) for f in range(n)]
-            for f in range(n):
-                assert np.array_equal(lev[f], want[f][1]), (W, H, q, legacy, f)
-                assert pay[f] == want[f][0], (W, H, q, legacy, f)
-            assert enc.encode_device(rgb).payloads() == pay          # production instantiation (no levels)
-            enc.close()
-    # 4-byte pixels
-    enc4 = M1Encoder(352, 240, 4, 0, 12, max_frames=2)
-    assert "k_encode_groups" in enc4.encode_kernel
-    rgb = M1Encoder(352, 240, 3, 0, 12, max_frames=2).synth_rgb(5, 0, 2, 0)
-    rgba = torch.cat([rgb, torch.full((2, 240, 352, 1), 9, dtype=torch.uint8, device=rgb.device)], dim=3).contiguous()
-    got = enc4.encode_device(rgba).payloads()
-    host = rgb.cpu().numpy()
-    assert got == [port.encode_picture(host[f], 12, 0) for f in range(2)]
 
 
 def test_tuning_arguments_are_validated():

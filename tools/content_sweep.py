@@ -14,8 +14,8 @@ from ec504_imageencoder_b200 import M1Encoder, MODE_FULL  # noqa: E402
 KINDS = {0: "natural", 1: "noise", 2: "grey", 3: "r==g"}
 
 
-def run(W, H, n, q, kind, steps=10, warm=3, legacy=False):
-    enc = M1Encoder(W, H, 3, MODE_FULL, q, max_frames=n, cta_per_chunk=legacy)
+def run(W, H, n, q, kind, steps=10, warm=3):
+    enc = M1Encoder(W, H, 3, MODE_FULL, q, max_frames=n)
     st = torch.cuda.Stream()
     with torch.cuda.stream(st):
         rgb = enc.synth_rgb(12345, 0, n, kind)
@@ -39,9 +39,8 @@ def run(W, H, n, q, kind, steps=10, warm=3, legacy=False):
     alg = 3 * W * H + payload + 4
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0
-    enc_name = enc.encode_kernel
     enc.close()
-    return {"kernel": enc_name, "width": W, "height": H, "frames": n, "quality": q, "content": KINDS[kind], "ms_per_pass": ms,
+    return {"width": W, "height": H, "frames": n, "quality": q, "content": KINDS[kind], "ms_per_pass": ms,
             "frames_per_s": fps, "payload_bytes_per_frame": payload, "encode_kernel_ms": kms[0] / steps,
             "encode_kernel_roofline_frac": alg * n / (kms[0] / steps * 1e-3) / 1e9 / peak}
 
@@ -50,10 +49,9 @@ if __name__ == "__main__":
     out = []
     for cfg in [(1920, 1080, 300, 12, 0), (1920, 1080, 300, 12, 1), (1920, 1080, 300, 12, 2), (1920, 1080, 300, 12, 3),
                 (1920, 1080, 300, 50, 1), (1920, 1080, 300, 50, 0)]:
-        for legacy in (False, True):
-            r = run(*cfg, legacy=legacy)
-            out.append(r)
-            print(json.dumps(r), flush=True)
+        r = run(*cfg)
+        out.append(r)
+        print(json.dumps(r), flush=True)
     tag = sys.argv[1] if len(sys.argv) > 1 else "sweep"
     with open(os.path.join(ROOT, "gpurun_out", f"content_{tag}.json"), "w") as f:
         json.dump(out, f, indent=1)
