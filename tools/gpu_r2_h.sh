@@ -1,0 +1,26 @@
+#!/bin/sh
+# round 2, call h: final 1-GPU evidence -- whole GPU suite, the bench line, the reference arm, the ncu launch list and
+# one --set full capture of k_encode_chunks (product build), and the folder-of-JPEGs wall times of the C driver.
+mkdir -p gpurun_out
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2h_smoke.txt 2>&1 || { tail -8 gpurun_out/r2h_smoke.txt; echo SMOKE_FAILED; exit 1; }
+tail -1 gpurun_out/r2h_smoke.txt
+timeout 1800 python -m pytest tests -m gpu -q 2>&1 | tail -12 > gpurun_out/r2h_pytest_1gpu.txt; cat gpurun_out/r2h_pytest_1gpu.txt
+python bench.py --steps 20 --warmup 5 2>gpurun_out/r2h_bench.err | tail -1 > gpurun_out/r2h_bench.json; tail -2 gpurun_out/r2h_bench.err
+python - <<'PY'
+import json
+d = json.load(open('gpurun_out/r2h_bench.json'))
+print('fps', round(d['value']), 'ms/step', round(d['ms_per_step'], 3), 'frac', round(d['roofline']['frac'], 4), d['roofline']['kernel_ms_per_step'],
+      'e2e', round(d['e2e']['value']), 'wc', round(d['e2e']['write_combined_input']['value']), d['clocks'], d['parity']['identical'], '/', d['parity']['frames_checked'])
+for o in d.get('other_configs', []):
+    print(' ', o['workload'], round(o['value']), 'frac', round(o['roofline']['frac'], 4), o['parity']['identical'], '/', o['parity']['frames_checked'])
+PY
+python bench.py --impl reference --steps 3 --warmup 1 | tail -1 > gpurun_out/r2h_reference_arm.json; cut -c1-200 gpurun_out/r2h_reference_arm.json
+python tools/folder_bench.py 300 > gpurun_out/r2h_folder_bench.json 2>gpurun_out/r2h_folder_bench.err; python -c "
+import json; d = json.load(open('gpurun_out/r2h_folder_bench.json'))
+for r in d['runs']: print(r['setting'], 'bit_files', r['bit_files'], 'rc', r['rc'], round(r['seconds'], 2), 's', round(r['pictures_per_s'], 1), 'pictures/s')"
+B="python bench.py --steps 2 --warmup 3 --frames 40 --no-cpu-baseline --no-other-configs"
+$B > gpurun_out/r2h_plain.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 9 -c 6 --csv --log-file gpurun_out/r2h_launches.csv $B > gpurun_out/r2h_ncu_launches.log 2>&1
+$B > gpurun_out/r2h_plain2.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_encode -s 3 -c 1 -o gpurun_out/r2h_prof $B > gpurun_out/r2h_ncu_full.log 2>&1
+tail -2 gpurun_out/r2h_ncu_full.log; grep -c k_ gpurun_out/r2h_launches.csv
