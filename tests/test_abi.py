@@ -97,3 +97,13 @@ def test_generated_tables_match_oracle(port):
             e = dc[sz + (0 if luma else 9)]
             code = format(e & 0xffffff, "0%db" % (e >> 24))
             assert port.block_bits(zz, luma) == code + "1" * sz + "10"
+
+
+def test_product_library_reads_no_environment():
+    """the product build of the CUDA library has no environment knobs (the work-partition
+    knobs are m1cu_create_ex arguments; the profiling knobs exist only in tools/build_experiments.sh builds)."""
+    lib = open(os.path.join(ROOT, "ec504_imageencoder_b200", "libm1cu.so"), "rb").read()
+    for knob in (b"M1_DEBUG_SKIP", b"M1_PAD_SMEM", b"M1_CHUNK_MBS", b"M1_WIN_WORDS", b"M1_WS", b"M1_PERSIST", b"M1_CHUNK_EVEN"):
+        assert knob not in lib, knob
+    for src in ("m1cu_api.cu", "m1cu_kernels.cu", "m1cu_block.cuh", "m1cu_colour.cuh", "m1cu_common.cuh"):
+        assert "getenv" not in open(os.path.join(ROOT, "ec504_imageencoder_b200", "csrc", src)).read(), src
