@@ -43,6 +43,11 @@ struct m1cu_ctx {
     bool own_stream = false;
     // device state
     uint32_t *d_staging = nullptr, *d_chunk_bits = nullptr, *d_chunk_dst = nullptr;
+    // second set + side stream: calls longer than batch_frames run the layout + stitch of one launch round
+    // beside the chunk encoder of the next (allocated by the first such call)
+    uint32_t *d_staging2 = nullptr, *d_chunk_bits2 = nullptr, *d_chunk_dst2 = nullptr;
+    cudaStream_t tail_stream = nullptr;
+    cudaEvent_t enc_done[2] = { nullptr, nullptr }, tail_done[2] = { nullptr, nullptr };
     M1Tables *d_tables = nullptr;
     // m1cu_assemble_stream: prefix templates (256 x 44) + prologue (27) on the device, the host copy they came from
     uint8_t *d_stream_tmpl = nullptr;
@@ -104,9 +109,10 @@ cudaEvent_t take_event(m1cu_ctx *ctx)
 
 // brackets one launch with events when timing is on
 struct Timed {
-    m1cu_ctx *c; int kind; cudaEvent_t a = nullptr;
-    Timed(m1cu_ctx *ctx, int k) : c(ctx), kind(k) { if (c->timing) { a = take_event(c); cudaEventRecord(a, c->stream); } }
-    ~Timed() { if (a) { cudaEvent_t b = take_event(c); cudaEventRecord(b, c->stream); c->spans.push_back({a, b, kind}); } }
+    m1cu_ctx *c; int kind; cudaStream_t s; cudaEvent_t a = nullptr;
+    Timed(m1cu_ctx *ctx, int k, cudaStream_t st = nullptr) : c(ctx), kind(k), s(st ? st : ctx->stream)
+    { if (c->timing) { a = take_event(c); cudaEventRecord(a, s); } }
+    ~Timed() { if (a) { cudaEvent_t b = take_event(c); cudaEventRecord(b, s); c->spans.push_back({a, b, kind}); } }
 };
 
 int ensure(m1cu_ctx *ctx, void **p, size_t *cap, size_t need, bool pinned = false)
@@ -237,6 +243,7 @@ int m1cu_create_ex(m1cu_ctx **out, int device, int width, int height, int channe
     if (batch < 1) batch = 1;
     if (batch > (size_t)max_frames) batch = (size_t)max_frames;
     if (batch > 65535) batch = 65535;                       // grid.z of k_encode_chunks / grid.y of k_stitch
+    if (tuning && tuning->batch_frames > 0 && (size_t)tuning->batch_frames < batch) batch = (size_t)tuning->batch_frames;
     ctx->batch_frames = (int)batch;
     CUC(cudaMalloc(&ctx->d_staging, per_frame * batch));
     CUC(cudaMalloc(&ctx->d_chunk_bits, sizeof(uint32_t) * g.chunks_per_frame * batch));
@@ -265,7 +272,11 @@ int m1cu_destroy(m1cu_ctx *ctx)
     if (!ctx) return M1CU_OK;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->tail_stream) cudaStreamSynchronize(ctx->tail_stream);
     cudaFree(ctx->d_staging); cudaFree(ctx->d_chunk_bits); cudaFree(ctx->d_chunk_dst);
+    cudaFree(ctx->d_staging2); cudaFree(ctx->d_chunk_bits2); cudaFree(ctx->d_chunk_dst2);
+    for (int i = 0; i < 2; ++i) { if (ctx->enc_done[i]) cudaEventDestroy(ctx->enc_done[i]); if (ctx->tail_done[i]) cudaEventDestroy(ctx->tail_done[i]); }
+    if (ctx->tail_stream) cudaStreamDestroy(ctx->tail_stream);
     cudaFree(ctx->d_tables); cudaFree(ctx->d_stream_tmpl); cudaFree(ctx->d_seg_off); cudaFree(ctx->d_stream); cudaFree(ctx->d_stream_end); cudaFree(ctx->d_err); cudaFree(ctx->d_running); cudaFree(ctx->d_done);
     cudaFree(ctx->d_in); cudaFree(ctx->d_out); cudaFree(ctx->d_fbytes); cudaFree(ctx->d_foff);
     cudaFree(ctx->d_levels); cudaFree(ctx->d_planes);
@@ -339,27 +350,59 @@ int m1cu_encode_device(m1cu_ctx *ctx, const uint8_t *d_rgb, int n_frames, uint8_
     CU(cudaMemsetAsync(ctx->d_running, 0, sizeof(unsigned long long), st));
     int bx = (g.chunks_per_frame + 7) / 8;                     // k_stitch: one warp per chunk, 8 warps per CTA
     if (bx > 512) bx = 512;
-    for (int f0 = 0; f0 < n_frames; f0 += ctx->batch_frames) {
+    const int rounds = (n_frames + ctx->batch_frames - 1) / ctx->batch_frames;
+    // More than one launch round (the staging memory is bounded): the layout + stitch of round r run on a side
+    // stream beside the chunk encoder of round r + 1, with two sets of staging / chunk arrays.  Everything is
+    // still ordered on the context's stream for the caller: it waits for the last tail before the call returns
+    // control of the stream.
+    const bool overlap = rounds > 1;
+    if (overlap && !ctx->d_staging2) {
+        const size_t per_frame = (size_t)g.chunks_per_frame * g.chunk_stride;
+        CU(cudaMalloc(&ctx->d_staging2, per_frame * (size_t)ctx->batch_frames));
+        CU(cudaMalloc(&ctx->d_chunk_bits2, sizeof(uint32_t) * g.chunks_per_frame * (size_t)ctx->batch_frames));
+        CU(cudaMalloc(&ctx->d_chunk_dst2, sizeof(uint32_t) * g.chunks_per_frame * (size_t)ctx->batch_frames));
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, hi));
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaEventCreateWithFlags(&ctx->enc_done[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&ctx->tail_done[i], cudaEventDisableTiming));
+        }
+    }
+    int r = 0;
+    for (int f0 = 0; f0 < n_frames; f0 += ctx->batch_frames, ++r) {
         const int nb = n_frames - f0 < ctx->batch_frames ? n_frames - f0 : ctx->batch_frames;
+        const int b = overlap ? (r & 1) : 0;
+        uint32_t *staging = b ? ctx->d_staging2 : ctx->d_staging;
+        uint32_t *cbits = b ? ctx->d_chunk_bits2 : ctx->d_chunk_bits;
+        uint32_t *cdst = b ? ctx->d_chunk_dst2 : ctx->d_chunk_dst;
+        cudaStream_t tail = overlap ? ctx->tail_stream : st;
+        if (overlap && r >= 2) CU(cudaStreamWaitEvent(st, ctx->tail_done[b], 0));   // set b has been stitched
         {
             Timed t(ctx, 0);
-            CU(m1k_launch_encode(g, ctx->q, d_rgb + (size_t)f0 * g.frame_stride, nb, ctx->d_tables, ctx->d_staging,
-                                 ctx->d_chunk_bits, d_levels ? d_levels + (size_t)f0 * g.mbs_per_frame * 384 : nullptr,
+            CU(m1k_launch_encode(g, ctx->q, d_rgb + (size_t)f0 * g.frame_stride, nb, ctx->d_tables, staging,
+                                 cbits, d_levels ? d_levels + (size_t)f0 * g.mbs_per_frame * 384 : nullptr,
                                  ctx->d_err, st));
         }
+        if (overlap) {
+            CU(cudaEventRecord(ctx->enc_done[b], st));
+            CU(cudaStreamWaitEvent(tail, ctx->enc_done[b], 0));
+        }
         {
-            Timed t(ctx, 1);
-            CU(m1k_launch_layout(g, nb, ctx->d_chunk_bits, ctx->d_chunk_dst, d_frame_bytes + f0,
+            Timed t(ctx, 1, tail);
+            CU(m1k_launch_layout(g, nb, cbits, cdst, d_frame_bytes + f0,
                                  (unsigned long long *)d_frame_offsets + f0, ctx->d_running, ctx->d_done,
-                                 (unsigned long long)out_cap, ctx->d_err, st));
+                                 (unsigned long long)out_cap, ctx->d_err, tail));
         }
         {
-            Timed t(ctx, 2);
-            CU(m1k_launch_stitch(g, nb, bx, ctx->d_staging, ctx->d_chunk_bits, ctx->d_chunk_dst, d_frame_bytes + f0,
-                                 (const unsigned long long *)d_frame_offsets + f0, d_out, (unsigned long long)out_cap, st));
+            Timed t(ctx, 2, tail);
+            CU(m1k_launch_stitch(g, nb, bx, staging, cbits, cdst, d_frame_bytes + f0,
+                                 (const unsigned long long *)d_frame_offsets + f0, d_out, (unsigned long long)out_cap, tail));
         }
+        if (overlap) CU(cudaEventRecord(ctx->tail_done[b], tail));
         ctx->launches += 3;
     }
+    if (overlap) CU(cudaStreamWaitEvent(st, ctx->tail_done[(rounds - 1) & 1], 0));     // the side stream is in order: this covers every round
     return M1CU_OK;
 }
 

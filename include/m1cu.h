@@ -83,6 +83,9 @@ typedef struct m1cu_tuning {
     int chunk_mbs;   /* macroblocks per CTA, 1..16 (default 16: full chunks + one shorter tail per slice) */
     int chunk_even;  /* != 0: equal chunks per slice instead                                            */
     int win_words;   /* shared-memory bit-window words per pass, 4..512 (default 512)                   */
+    int batch_frames;/* pictures per launch round, > 0 lowers the default (about 2 GiB of staging); a call
+                        with more pictures runs several rounds, layout + stitch of one beside the encode
+                        of the next                                                                     */
 } m1cu_tuning;
 int  m1cu_create_ex(m1cu_ctx **out, int device, int width, int height, int channels,
                     int mode, int quality_factor, int max_frames, const m1cu_tuning *tuning);

@@ -17,7 +17,8 @@ CASES = ((352, 240, 3, 12, 0), (1920, 1080, 2, 12, 0), (640, 480, 2, 50, 1), (19
 
 
 @pytest.mark.parametrize("tuning", [{"chunk_mbs": 7}, {"chunk_mbs": 1}, {"chunk_mbs": 11}, {"chunk_even": True},
-                                    {"win_words": 8}, {"win_words": 5, "chunk_mbs": 3}, {"win_words": 6, "chunk_mbs": 5}])
+                                    {"win_words": 8}, {"win_words": 5, "chunk_mbs": 3}, {"win_words": 6, "chunk_mbs": 5},
+                                    {"batch_frames": 1}, {"batch_frames": 2, "chunk_mbs": 5}])
 def test_kernel_variant(tuning, port):
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
@@ -33,6 +34,37 @@ def test_kernel_variant(tuning, port):
             assert np.array_equal(lev[f], rl), (W, H, f)
             assert pay[f] == rp and pay2[f] == rp, (W, H, f)
         enc.close()
+
+
+def test_launch_rounds_overlap(port):
+    """A call with more pictures than one launch round holds (batch_frames) runs the layout + stitch of a round on a
+    side stream beside the next round's chunk encoder, on two sets of staging buffers: 23 pictures in rounds of 4,
+    twice in a row on the same context (buffer reuse across calls), levels and bytes against the oracle; the
+    host-buffer paths on top of it."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from ec504_imageencoder_b200 import M1Encoder
+    W, H, n, q = 352, 240, 23, 12
+    enc = M1Encoder(W, H, 3, 0, q, max_frames=n, batch_frames=4)
+    rgb = enc.synth_rgb(31, 0, n, 0)
+    host = rgb.cpu().numpy()
+    want = [port.encode_picture(host[f], q, 0, want_levels=True) for f in range(n)]
+    for _ in range(2):
+        res = enc.encode_device(rgb, want_levels=True)
+        pay, lev = res.payloads(), res.levels.cpu().numpy()
+        for f in range(n):
+            assert np.array_equal(lev[f], want[f][1]), f
+            assert pay[f] == want[f][0], f
+    res_a = enc.alloc_outputs(n)
+    res_b = enc.alloc_outputs(9)
+    enc.encode_device(rgb, res=res_a, check=False)            # two calls queued back to back, no host sync between
+    enc.encode_device(rgb[:9], res=res_b, check=False)
+    enc.check()
+    assert res_a.payloads() == [w[0] for w in want]
+    assert res_b.payloads() == [w[0] for w in want[:9]]
+    hp, _ = enc.encode_host(host)
+    assert hp == [w[0] for w in want]
+    enc.close()
 
 
 def test_tuning_arguments_are_validated():
