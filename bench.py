@@ -577,6 +577,9 @@ def run_ours(args):
                                   "chain + int32 DCT + VLC cost about 60 issue slots per pixel (DESIGN.md section 7)"),
                          "kernel_ms_per_step": head["kernel_ms_per_step"]},
         }
+        line["memcheck"] = ("compute-sanitizer is closed on this pool: no memcheck / racecheck run of the kernels exists; evidence is the "
+                            "bit-exact parity suite (every geometry, both modes, odd sizes, multi-window chunks) and, for the host C, "
+                            "ASan + UBSan (profiles/r2_host_sanitizers.txt: clean)")
         if head["gather"] is not None:
             line["gather_verified"] = head["gather"]["gather_verified"]
             line["ranks"] = head["gather"]["ranks"]
