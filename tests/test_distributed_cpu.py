@@ -74,3 +74,16 @@ def test_gather_to_rank0_gloo(world, n_frames):
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_frame_range_partitions_baseline_configs():
+    """BASELINE configs[3] (8000 frames over 2 / 4 / 8 ranks) and configs[4] (120 frames over 8): the ranges are
+    contiguous, disjoint, ordered and cover the sequence; uneven counts differ by at most one frame."""
+    from ec504_imageencoder_b200.distributed import frame_range
+    for total, worlds in ((8000, (1, 2, 4, 8)), (120, (2, 4, 8)), (7, (2, 3, 8)), (0, (2,))):
+        for w in worlds:
+            edges = [frame_range(k, w, total) for k in range(w)]
+            assert edges[0][0] == 0 and edges[-1][1] == total
+            assert all(edges[k][1] == edges[k + 1][0] for k in range(w - 1))
+            sizes = [hi - lo for lo, hi in edges]
+            assert min(sizes) >= 0 and max(sizes) - min(sizes) <= 1

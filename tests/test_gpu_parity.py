@@ -52,6 +52,14 @@ def test_ragged_sizes(m1, port, W, H):
     _encode_both(m1, port, W, H, 1, 50, SYNTH_NATURAL)
 
 
+@pytest.mark.parametrize("W,H", [(65535, 16), (65520, 32), (16, 65535), (32, 16384), (8192, 8192)])
+def test_extreme_geometries(m1, port, W, H):
+    """The largest width / height the context accepts (65535: 4096 macroblocks per slice = 256 chunks, or 4096 slices,
+    whose vertical position byte wraps 16 times: source/mpeg1_blk.c:12-20 writes (vertical_pos + 1) & 0xff) and a
+    67-megapixel square picture."""
+    _encode_both(m1, port, W, H, 1, 12, SYNTH_NOISE)
+
+
 @pytest.mark.parametrize("q", [1, 12, 50, 75, 89])
 def test_ref_compat(m1, port, q):
     """Literal traversal of include/encoder.h:238-443 on a 400x600 picture (the fixture size)."""
