@@ -210,6 +210,11 @@ int m1cu_create_ex(m1cu_ctx **out, int device, int width, int height, int channe
         const int last_mbs = g.mbs_per_slice - (g.chunks_per_slice - 1) * g.chunk_mbs;
         g.inv_nbc[0] = (65536u + 2u * g.chunk_mbs - 1u) / (2u * g.chunk_mbs);
         g.inv_nbc[1] = (65536u + 2u * last_mbs - 1u) / (2u * last_mbs);
+        // A short last chunk (1080p: 120 = 7 x 16 + 8) would hold a whole CTA slot for half a CTA's work: when two
+        // of them fit one chunk, the last chunks of slices 2k and 2k+1 share a CTA (k_encode_chunks).
+        g.pair_tails = (mode == M1CU_MODE_FULL && g.chunks_per_slice >= 2 && g.slices >= 2 && 2 * last_mbs <= g.chunk_mbs &&
+                        !(tuning && tuning->no_tail_pairing)) ? last_mbs : 0;
+        g.inv_nbc[2] = (65536u + 4u * last_mbs - 1u) / (4u * last_mbs);
     }
     g.chunk_stride = (unsigned)align_up(((size_t)M1_SLICE_HDR_BITS + (size_t)g.chunk_mbs * M1_MB_MAX_BITS + 7) / 8 + 8, 16);
     g.frame_stride = (unsigned long long)width * height * channels;

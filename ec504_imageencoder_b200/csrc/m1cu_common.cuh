@@ -35,8 +35,10 @@ struct M1Geom {
     int chunks_per_slice;
     int chunks_per_frame;
     int mbs_per_frame;
-    unsigned inv_nbc[2];       // ceil(2^16 / block columns) of a full chunk [0] and of a slice's last chunk [1]:
-                               // x / nbc == (x * inv) >> 16 for x < 2048 (splits a half-tile index without a division)
+    int pair_tails;            // > 0: the last chunk of a slice holds at most chunk_mbs / 2 macroblocks (= this value), and
+                               // ONE CTA encodes the last chunks of slices 2k and 2k+1 together (FULL mode only)
+    unsigned inv_nbc[3];       // ceil(2^16 / block columns) of a full chunk [0], of a slice's last chunk [1] and of a
+                               // pair of last chunks [2]: x / nbc == (x * inv) >> 16 for x < 2048
     unsigned chunk_stride;     // staging bytes per chunk (multiple of 16)
     unsigned long long frame_stride;   // input bytes per picture
 };

@@ -211,13 +211,6 @@ __device__ __noinline__ void color_half_tile_generic(const uint8_t *__restrict__
 // -------------------------------------------------------------------------------------------
 // kLoad: 3 / 4 = FULL mode with aligned 3- / 4-byte pixels (fast half-tiles), 0 = FULL mode generic
 // loads only, -1 = REF_COMPAT.  One instantiation per input format keeps each kernel's code small.
-// Timing experiment only (tools/, garbage output): M1X_NO_BARRIER replaces the CTA barriers of k_encode_chunks by warp
-// barriers to measure what the barrier waits cost.
-#if defined(M1_EXPERIMENTS) && defined(M1X_NO_BARRIER)
-#define M1_ENC_BARRIER() __syncwarp()
-#else
-#define M1_ENC_BARRIER() __syncthreads()
-#endif
 #ifndef M1_ENC_MIN_CTAS
 #define M1_ENC_MIN_CTAS 7   // 72 registers: 7 CTAs/SM measured best (6: -1.3 %, 8: -4 %, spills)
 #endif
@@ -233,14 +226,21 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     const int chunk = blockIdx.x, slice = blockIdx.y, frame = blockIdx.z;
     const int C = g.chunk_mbs;
     const int mb0 = chunk * C;
-    const int nmb = min(C, g.mbs_per_slice - mb0);
+    // Paired last chunks (g.pair_tails = T macroblocks each): the CTA of an even slice also encodes the last chunk
+    // of the next slice -- macroblock slots 0 .. T-1 are slice `slice`, slots T .. 2T-1 slice `slice + 1`, each
+    // with its own staging record; the odd slice's own CTA has nothing to do.
+    const bool last_chunk = chunk == g.chunks_per_slice - 1;
+    const int T = (kLoad >= 0 && last_chunk) ? g.pair_tails : 0;
+    if (T && (slice & 1)) return;
+    const bool paired = T && slice + 1 < g.slices;
+    const int nmb = paired ? 2 * T : min(C, g.mbs_per_slice - mb0);
 
     // shared memory carve-up
     int *planes = (int *)smem;                                   // [6C blocks][64] int32, swizzled
     short *rec = (short *)smem;                                  // aliases planes (see layout note)
     uint32_t *win = (uint32_t *)(planes + 6 * C * 64);           // [M1_WIN_WORDS + 4]
     M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS + 4);         // 16-byte aligned
-    int *wtot = (int *)(tb + 1);                                 // [8] bits per warp, 16-byte aligned
+    int *wtot = (int *)(tb + 1);                                 // [12]: [0..3] bits per warp, [4..7] fix-up queue lengths, [8] pair split; 16-byte aligned
 
     // Per-CTA prologue, kept short: the coder's tables up to zofs[] in 128-bit pieces (the non-zero
     // keys come from the constant bank), and only the first blockDim.x window words zeroed -- a chunk
@@ -274,11 +274,12 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         const size_t pitch = (size_t)g.W * g.channels;
         const int nbc = 2 * nmb;
         constexpr int kCh = kLoad > 0 ? kLoad : 3;
-        const unsigned inv = (chunk == g.chunks_per_slice - 1) ? g.inv_nbc[1] : g.inv_nbc[0];
+        const unsigned inv = paired ? g.inv_nbc[2] : last_chunk ? g.inv_nbc[1] : g.inv_nbc[0];
         for (int st = tid; st < 4 * nbc; st += nthr) {
             const int q4 = (int)(((unsigned)st * inv) >> 16), bc = st - q4 * nbc;
-            const int x0 = 16 * mb0 + 8 * bc;
-            int y = 16 * slice + 4 * q4;
+            const int sub = (paired && bc >= 2 * T) ? 1 : 0;  // second slice of a pair
+            const int x0 = 16 * mb0 + 8 * (bc - sub * 2 * T);
+            int y = 16 * (slice + sub) + 4 * q4;
             if (kLoad > 0 && x0 + 8 <= g.W) {
                 // rows below the picture replicate its last row (edge replication up to the coded size):
                 // clamp the first row, then step by the pitch only while the next row exists
@@ -325,7 +326,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
             planes[plane_word(5 * C + mb, r, c, C)] = cr;
         }
     }
-    M1_ENC_BARRIER();
+    __syncthreads();
     if (M1_COLOUR_SPLIT != 2 && kLoad > 0) {
         // Fix-up pass of the integer colour path: the queued quads again, by the reference's double chain
         // (their pixels are L1/L2 hits).  One quad per thread, so the cost follows the NUMBER of flagged
@@ -335,15 +336,16 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         const int nfix = fc.x + fc.y + fc.z + fc.w;
         if (nfix) {
             const int nbc = 2 * nmb;
-            const unsigned inv = (chunk == g.chunks_per_slice - 1) ? g.inv_nbc[1] : g.inv_nbc[0];
+            const unsigned inv = paired ? g.inv_nbc[2] : last_chunk ? g.inv_nbc[1] : g.inv_nbc[0];
             for (int e = tid; e < nfix; e += nthr) {
                 int qi = e, qw = 0;                         // entry qi of warp qw's queue
                 if (qi >= fc.x) { qi -= fc.x; qw = 1; if (qi >= fc.y) { qi -= fc.y; qw = 2; if (qi >= fc.z) { qi -= fc.z; qw = 3; } } }
                 const int code = ((const unsigned short *)win)[256 * qw + qi], st = code >> 3, h = (code >> 2) & 1, q = code & 3;
                 const int q4 = (int)(((unsigned)st * inv) >> 16), bc = st - q4 * nbc;
-                color_quad_exact(fr, g, 16 * mb0 + 8 * bc, 16 * slice + 4 * q4 + 2 * h, bc, 2 * q4 + h, q, C, planes);
+                const int sub = (paired && bc >= 2 * T) ? 1 : 0;
+                color_quad_exact(fr, g, 16 * mb0 + 8 * (bc - sub * 2 * T), 16 * (slice + sub) + 4 * q4 + 2 * h, bc, 2 * q4 + h, q, C, planes);
             }
-            M1_ENC_BARRIER();
+            __syncthreads();
         }
     }
     win[tid] = 0;                                           // the queue is consumed: `win` becomes the bit window
@@ -399,7 +401,9 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         if (lane >= d) incl += t;
     }
     if (lane == 31) wtot[warp] = incl;
-    M1_ENC_BARRIER();
+    const int t2 = 6 * T;                                    // first thread of the second record of a pair
+    if (paired && tid == t2) wtot[8] = incl - my_bits;       // its exclusive prefix inside its warp
+    __syncthreads();
 
     if (kLevels) {
         // debug output: quantised zigzag levels in coding order, [picture][macroblock][6][64]
@@ -407,27 +411,37 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         for (int i = tid; i < nmb * 384; i += nthr) {
             const int p = i >> 6, z = i & 63, m = p / 6, b = p - m * 6;
             const int t = b < 4 ? (b >> 1) * 2 * C + 2 * m + (b & 1) : b * C + m;
-            dst[i] = (short)quant_level(rec[rec_index(t, z, p & 7)], z, tb);   // p = 6 * m + b = the block's thread
+            // slot m of a pair's second half is macroblock m - T of the NEXT slice
+            const size_t o = (paired && m >= T) ? (size_t)(g.mbs_per_slice - T) * 384 : 0;
+            dst[o + i] = (short)quant_level(rec[rec_index(t, z, p & 7)], z, tb);   // p = 6 * m + b = the block's thread
         }
     }
 
     const int hdr_bits = chunk == 0 ? M1_SLICE_HDR_BITS : 0;
     const int4 wt = *(const int4 *)wtot;                    // blockDim.x <= 128: at most four warps
-#if defined(M1_EXPERIMENTS) && defined(M1X_NO_BARRIER)
-    const int total_bits = min(hdr_bits + wt.x + wt.y + wt.z + wt.w, 8192) & 0x3fff;   // racy garbage stays bounded
-#else
-    const int total_bits = hdr_bits + wt.x + wt.y + wt.z + wt.w;
-#endif
+    const int real_bits = hdr_bits + wt.x + wt.y + wt.z + wt.w;
     const int base = hdr_bits + (warp > 0 ? wt.x : 0) + (warp > 1 ? wt.y : 0) + (warp > 2 ? wt.z : 0);
-    const int my_off = base + incl - my_bits;
+    // A pair's second record starts on a fresh 32-bit word of the (virtual) bit string the window passes walk:
+    // bits0 = bits of the first record, gap = the padding in front of the second.
+    int bits0 = real_bits, gap = 0;
+    if (paired) {
+        const int w2 = t2 >> 5;
+        bits0 = (w2 > 0 ? wt.x : 0) + (w2 > 1 ? wt.y : 0) + (w2 > 2 ? wt.z : 0) + wtot[8];   // (a last chunk has no slice header)
+        gap = (32 - (bits0 & 31)) & 31;
+    }
+    const int total_bits = real_bits + gap;
+    const int my_off = base + incl - my_bits + ((paired && tid >= t2) ? gap : 0);
 
-    uint32_t *out = staging + ((size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk)
-                                  * (g.chunk_stride / 4);
+    const size_t rec0 = (size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk;
+    uint32_t *out = staging + rec0 * (g.chunk_stride / 4);
+    // word v of the virtual bit string -> its place in the staging records
+    const int vsplit = paired ? (bits0 + gap) >> 5 : 0x7fffffff;
+    uint32_t *out2 = staging + (rec0 + g.chunks_per_slice) * (g.chunk_stride / 4) - (paired ? vsplit : 0);
     const int WW = g.win_words;                             // <= M1_WIN_WORDS (smaller only in tests)
     if (min(WW, (total_bits + 31) >> 5) + 2 > nthr) {       // uniform; rare at typical qualities
 #pragma unroll 1
         for (int i = nthr + tid; i < WW + 2; i += nthr) win[i] = 0;
-        M1_ENC_BARRIER();
+        __syncthreads();
     }
     for (int w0 = 0;; w0 += 32 * WW) {            // the window words in use are zero here
         if (tid == 0 && hdr_bits && w0 == 0) {
@@ -451,18 +465,23 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                 code_block(ww, rec, pb, nz, is_luma, tb, tid & 7);
             }
         }
-        M1_ENC_BARRIER();
+        __syncthreads();
         const int nwords = min(WW, (total_bits - w0 + 31) >> 5);
 #pragma unroll 1
-        for (int i = tid; i < nwords; i += nthr) out[(w0 >> 5) + i] = win[i];
+        for (int i = tid; i < nwords; i += nthr) {
+            const int v = (w0 >> 5) + i;
+            (v < vsplit ? out : out2)[v] = win[i];
+        }
         if (w0 + 32 * WW >= total_bits) break;
-        M1_ENC_BARRIER();                                    // rare: the chunk needs another window pass
+        __syncthreads();                                    // rare: the chunk needs another window pass
 #pragma unroll 1
         for (int i = tid; i < WW + 2; i += nthr) win[i] = 0;
-        M1_ENC_BARRIER();
+        __syncthreads();
     }
-    if (tid == 0)
-        chunk_bits[(size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk] = (uint32_t)total_bits;
+    if (tid == 0) {
+        chunk_bits[rec0] = (uint32_t)bits0;
+        if (paired) chunk_bits[rec0 + g.chunks_per_slice] = (uint32_t)(real_bits - bits0);
+    }
 }
 
 // -------------------------------------------------------------------------------------------
@@ -765,7 +784,7 @@ size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
 #else
     const size_t pad = 0;
 #endif
-    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 4) * 4 + sizeof(M1Tables) + 8 * sizeof(int) + 16 + pad;
+    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 4) * 4 + sizeof(M1Tables) + 12 * sizeof(int) + 16 + pad;
 }
 
 int m1k_encode_threads(const M1Geom &g) { return (8 * g.chunk_mbs + 31) & ~31; }   // one colour tile per thread; 6C of them own a block

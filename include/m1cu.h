@@ -83,6 +83,8 @@ typedef struct m1cu_tuning {
     int chunk_mbs;   /* macroblocks per CTA, 1..16 (default 16: full chunks + one shorter tail per slice) */
     int chunk_even;  /* != 0: equal chunks per slice instead                                            */
     int win_words;   /* shared-memory bit-window words per pass, 4..512 (default 512)                   */
+    int no_tail_pairing; /* != 0: every slice's short last chunk gets its own CTA (default: two of them share one
+                            when they fit a chunk together, e.g. 1080p: 120 macroblocks = 7 x 16 + 8)          */
     int batch_frames;/* pictures per launch round, > 0 lowers the default (about 2 GiB of staging); a call
                         with more pictures runs several rounds, layout + stitch of one beside the encode
                         of the next                                                                     */

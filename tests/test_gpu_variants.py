@@ -13,12 +13,17 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-CASES = ((352, 240, 3, 12, 0), (1920, 1080, 2, 12, 0), (640, 480, 2, 50, 1), (1920, 1080, 1, 5, 1), (48, 32, 2, 12, 1))
+# (1080p: 120 macroblocks per slice = 7 x 16 + 8, SIF: 22 = 16 + 6, 640: 40 = 2 x 16 + 8 -> paired last chunks by default;
+#  352x240 has an odd number of slices, so its last slice's short chunk stays alone; 89 = long blocks: multi-pass windows)
+CASES = ((352, 240, 3, 12, 0), (1920, 1080, 2, 12, 0), (640, 480, 2, 50, 1), (1920, 1080, 1, 5, 1), (48, 32, 2, 12, 1),
+         (1920, 1088, 1, 89, 1), (352, 256, 2, 89, 1))
 
 
 @pytest.mark.parametrize("tuning", [{"chunk_mbs": 7}, {"chunk_mbs": 1}, {"chunk_mbs": 11}, {"chunk_even": True},
                                     {"win_words": 8}, {"win_words": 5, "chunk_mbs": 3}, {"win_words": 6, "chunk_mbs": 5},
-                                    {"batch_frames": 1}, {"batch_frames": 2, "chunk_mbs": 5}])
+                                    {"batch_frames": 1}, {"batch_frames": 2, "chunk_mbs": 5},
+                                    {"no_tail_pairing": True}, {"no_tail_pairing": True, "win_words": 8},
+                                    {"chunk_mbs": 14}, {"chunk_mbs": 14, "win_words": 4}, {"chunk_mbs": 9, "win_words": 7}])
 def test_kernel_variant(tuning, port):
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
