@@ -23,7 +23,16 @@ extern void stbi_image_free(void *retval_from_stbi_load);
 extern const char *stbi_failure_reason(void);
 extern int stbi_info(char const *filename, int *x, int *y, int *comp);
 
-#define M1_BATCH 32      /* pictures per GPU call of m1_encode_frames_to_file / _to_memory */
+
+/* Pictures per GPU call: about 384 MB of input, so that 1080p batches (64 pictures) reach the overlapped
+ * upload / encode / download path of m1cu_encode_host, at most 256 and at least 1. */
+static int batch_size(size_t frame_bytes, int count)
+{
+    size_t b = ((size_t)384 << 20) / (frame_bytes ? frame_bytes : 1);
+    if (b < 1) b = 1;
+    if (b > 256) b = 256;
+    return (int)b < count ? (int)b : count;
+}
 
 static int env_int(const char *name, int dflt)
 {
@@ -140,7 +149,7 @@ static int encode_frames(const unsigned char *frames, int n_frames, int width, i
 {
     if (!frames || n_frames <= 0) return M1CU_ERR_ARG;
     m1cu_ctx *ctx = NULL;
-    const int batch = n_frames < M1_BATCH ? n_frames : M1_BATCH;
+    const int batch = batch_size((size_t)width * height * channels, n_frames);
     int rc = m1cu_create(&ctx, env_int("M1_DEVICE", 0), width, height, channels, mode, quality, batch);
     if (rc != M1CU_OK) { printf("Error: cannot create the GPU encoder (%d): %s\n", rc, m1cu_last_error(NULL)); return rc; }
     const size_t cap = (m1cu_payload_bound(ctx) + 48) * (size_t)batch;   /* + headers and trailer when the GPU assembles the stream */
@@ -192,16 +201,6 @@ static void write_bit_files(m1cu_ctx *ctx, const char *folder, long first_index,
         snprintf(name, sizeof name, "%s/image_%ld.bit", folder, first_index + i + 1);
         write_to_bitstream(name, p, p + np, p + 2 * np, width, height);
     }
-}
-
-/* Pictures per GPU call: about 384 MB of input, so that 1080p batches (64 pictures) reach the overlapped
- * upload / encode / download path of m1cu_encode_host, at most 256 and at least 1. */
-static int batch_size(size_t frame_bytes, int count)
-{
-    size_t b = ((size_t)384 << 20) / (frame_bytes ? frame_bytes : 1);
-    if (b < 1) b = 1;
-    if (b > 256) b = 256;
-    return (int)b < count ? (int)b : count;
 }
 
 /* ---- decode pipeline ---------------------------------------------------------------------------------

@@ -174,13 +174,13 @@ def test_driver_stream_equals_oracle(host, port):
 def test_driver_with_device_stream_assembly(host, port, monkeypatch):
     """M1_DEVICE_STREAM=1: the driver lets the GPU place headers, payloads and trailers
     (m1cu_encode_host_stream) and writes each batch with one call; same bytes as the oracle's stream,
-    also across the driver's 32-picture batches."""
+    also across the driver's batches (at most 256 pictures each)."""
     torch = pytest.importorskip("torch")
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
     monkeypatch.setenv("M1_DEVICE_STREAM", "1")
     for (W, H, n, q, mode, kind) in ((352, 240, 5, 12, 0, 0), (100, 70, 3, 50, 0, 1), (400, 600, 3, 12, 1, 1),
-                                     (96, 64, 70, 12, 0, 0)):
+                                     (96, 64, 300, 12, 0, 0)):
         frames = np.stack([port.synth_rgb(77, f, W, H, kind) for f in range(n)])
         assert host.encode_frames_to_memory(frames, q, mode) == port.encode_stream(frames, q, mode)
 
