@@ -72,6 +72,19 @@ __device__ __forceinline__ void chroma_from_doubles(double rd, double gd, double
     v = __dsub_rn(v, __dmul_rn(kYcc[6], bd));
     cr = trunc_nonneg(v);
 }
+// Chroma of one pixel ADDED to running sums kept in the 2^52 form (see convert_half_tile_exact): accb / accr are
+// 2^52 + (sum so far); RZ(u + acc) = acc + trunc(u) exactly because u >= 0 and the result is an integer-spaced double.
+__device__ __forceinline__ void chroma_accumulate(double rd, double gd, double bd, double &accb, double &accr)
+{
+    double u = __dsub_rn(128.0, __dmul_rn(kYcc[3], rd));
+    u = __dsub_rn(u, __dmul_rn(kYcc[4], gd));
+    u = __fma_rn(0.5, bd, u);
+    accb = __dadd_rz(u, accb);
+    double v = __fma_rn(0.5, rd, 128.0);
+    v = __dsub_rn(v, __dmul_rn(kYcc[5], gd));
+    v = __dsub_rn(v, __dmul_rn(kYcc[6], bd));
+    accr = __dadd_rz(v, accr);
+}
 __device__ __forceinline__ void ycbcr_from_doubles(double rd, double gd, double bd, int &y, int &cb, int &cr)
 {
     y = luma_from_doubles(rd, gd, bd);

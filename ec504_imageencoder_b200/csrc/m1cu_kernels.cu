@@ -5,8 +5,19 @@
 #include "m1cu_block.cuh"
 #include "m1cu_colour.cuh"
 #include "m1cu_quant.h"
+#include <vector>
+#include <stdio.h>
 #ifdef M1_EXPERIMENTS
 #include "../../tools/experiments/m1x_env.h"
+// Profiling build only: per-CTA phase timeline (M1_TRACE) and a first-wave start stagger (M1_STAGGER_NS).
+__device__ unsigned long long *m1x_trace;       // [CTA][4]: (smid << 48 | start), end of colour, end of blocks, end   (globaltimer ns)
+__device__ unsigned int m1x_sm_arrivals[1024];  // CTAs that have started on each SM in this launch
+__device__ int m1x_stagger_ns, m1x_stagger_ctas;
+__device__ __forceinline__ unsigned long long m1x_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned m1x_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
+#define M1X_MARK(slot) do { if (m1x_trace && threadIdx.x == 0) m1x_trace[4 * m1x_lin + (slot)] = (m1x_now() & 0xffffffffffffull) | ((slot) == 0 ? (unsigned long long)m1x_smid() << 48 : 0ull); } while (0)
+#else
+#define M1X_MARK(slot) do { } while (0)
 #endif
 
 // -------------------------------------------------------------------------------------------
@@ -176,6 +187,47 @@ __device__ __forceinline__ uint32_t color_half_tile(const uint8_t *__restrict__ 
     return convert_half_tile<CH>(load_half_tile<CH>(row0, pitch), bc, qy, C, planes);
 }
 
+// The product's half-tile (M1_COLOUR_SPLIT == 2): every pixel by the reference's double chain.  Two things keep
+// the non-FP64 instruction count down:
+//  * the 2x2 chroma sums are formed by the truncating adds themselves: trunc(x) is read from the low word of
+//    RZ(x + 2^52), and RZ(x' + (2^52 + s)) = 2^52 + s + trunc(x') exactly (the sum is an integer-spaced double,
+//    x' >= 0), so chaining the four pixels of a quad through one accumulator leaves cb0 + cb1 + cb2 + cb3 in the
+//    low word with no integer add at all;
+//  * the three swizzled shared-memory addresses come in precomputed (a1: the strip's first luma chunk of this
+//    half-tile, acb / acr: its chroma chunk): the caller derives the second half-tile's from the first by one XOR.
+template <int CH>
+__device__ __forceinline__ void convert_half_tile_exact(const HalfTilePixels<CH> px, int a1, int acb, int acr,
+                                                        int *__restrict__ planes)
+{
+    const uint32_t (&w)[2][2 * CH] = px.w;
+    int sb[4], sr[4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {                     // 4-pixel groups = 16-byte luma chunks, two 2x2 quads each
+        int yv[2][4];
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+            double accb = 4503599627370496.0, accr = 4503599627370496.0;
+#pragma unroll
+            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int e = 2 * h2 + dx, byte0 = CH * (4 * j + e);
+                    const double rd = byte_to_double(w[dy][byte0 >> 2], byte0 & 3);
+                    const double gd = byte_to_double(w[dy][(byte0 + 1) >> 2], (byte0 + 1) & 3);
+                    const double bd = byte_to_double(w[dy][(byte0 + 2) >> 2], (byte0 + 2) & 3);
+                    yv[dy][e] = luma_from_doubles(rd, gd, bd);
+                    chroma_accumulate(rd, gd, bd, accb, accr);
+                }
+            sb[2 * j + h2] = __double2loint(accb) >> 2;
+            sr[2 * j + h2] = __double2loint(accr) >> 2;
+        }
+        *(int4 *)(planes + (a1 ^ (j << 2))) = make_int4(yv[0][0], yv[0][1], yv[0][2], yv[0][3]);
+        *(int4 *)(planes + (a1 ^ ((2 + j) << 2))) = make_int4(yv[1][0], yv[1][1], yv[1][2], yv[1][3]);
+    }
+    *(int4 *)(planes + acb) = make_int4(sb[0], sb[1], sb[2], sb[3]);
+    *(int4 *)(planes + acr) = make_int4(sr[0], sr[1], sr[2], sr[3]);
+}
+
 // One 2x2 pixel quad by the exact double chain: any alignment / channel count, coordinates clamped to
 // the picture (= edge replication up to the coded size).  (x0, y0): top-left pixel of the half-tile,
 // qx: quad 0..3 inside it.  Used by the generic half-tile and by the fix-up pass of the fast path.
@@ -234,6 +286,20 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     if (T && (slice & 1)) return;
     const bool paired = T && slice + 1 < g.slices;
     const int nmb = paired ? 2 * T : min(C, g.mbs_per_slice - mb0);
+#ifdef M1_EXPERIMENTS
+    const size_t m1x_lin = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (m1x_stagger_ns) {                                        // the k-th CTA to start on an SM waits k * stagger (first wave only)
+        if (threadIdx.x == 0) {
+            const unsigned k = atomicAdd(&m1x_sm_arrivals[m1x_smid()], 1u);
+            if (k < (unsigned)m1x_stagger_ctas) {
+                const unsigned long long t0 = m1x_now(), d = (unsigned long long)k * m1x_stagger_ns;
+                while (m1x_now() - t0 < d) __nanosleep(200);
+            }
+        }
+        __syncthreads();
+    }
+    M1X_MARK(0);
+#endif
 
     // shared memory carve-up
     int *planes = (int *)smem;                                   // [6C blocks][64] int32, swizzled
@@ -285,6 +351,22 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                 // clamp the first row, then step by the pitch only while the next row exists
                 const int last = g.H - 1;
                 const uint8_t *row = fr + (size_t)min(y, last) * pitch + (size_t)x0 * kCh;
+#if M1_COLOUR_SPLIT == 2
+                // swizzled addresses of half-tile 0 (qy = 2 * q4): luma chunk i0 = 8 * (q4 & 1) of block (q4 >> 1, bc),
+                // chroma chunk 4 * q4 + (bc & 1) of the macroblock's Cb / Cr block; half-tile 1 toggles chunk bit 2
+                // (luma) / bit 1 (chroma), i.e. one XOR on the word address
+                const int by = q4 >> 1, k = bc >> 1;
+                const int a1 = chunk_word_keyed(by * 2 * C + bc, (q4 & 1) << 3, (6 * k + 2 * by + (bc & 1)) & 7);
+                const int kc = (6 * k + 4) & 7;       // key of the Cb block; the Cr block (thread + 1) has kc ^ 1
+                const int acb = chunk_word_keyed(4 * C + k, 4 * q4 + (bc & 1), kc);
+                const int acr = chunk_word_keyed(5 * C + k, 4 * q4 + (bc & 1), kc ^ 1);
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h, y += 2) {
+                    const size_t rp = (y + 1 <= last) ? pitch : 0;
+                    convert_half_tile_exact<kCh>(load_half_tile<kCh>(row, rp), a1 ^ (h << 4), acb ^ (h << 3), acr ^ (h << 3), planes);
+                    row += rp + ((y + 2 <= last) ? pitch : 0);
+                }
+#else
 #pragma unroll 1
                 for (int h = 0; h < 2; ++h, y += 2) {
                     const size_t rp = (y + 1 <= last) ? pitch : 0;
@@ -298,6 +380,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                     }
                     row += rp + ((y + 2 <= last) ? pitch : 0);
                 }
+#endif
             } else {
                 color_half_tile_generic(fr, g, x0, y, bc, 2 * q4, C, planes);
                 color_half_tile_generic(fr, g, x0, y + 2, bc, 2 * q4 + 1, C, planes);
@@ -327,6 +410,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         }
     }
     __syncthreads();
+    M1X_MARK(1);
     if (M1_COLOUR_SPLIT != 2 && kLoad > 0) {
         // Fix-up pass of the integer colour path: the queued quads again, by the reference's double chain
         // (their pixels are L1/L2 hits).  One quad per thread, so the cost follows the NUMBER of flagged
@@ -404,6 +488,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     const int t2 = 6 * T;                                    // first thread of the second record of a pair
     if (paired && tid == t2) wtot[8] = incl - my_bits;       // its exclusive prefix inside its warp
     __syncthreads();
+    M1X_MARK(2);
 
     if (kLevels) {
         // debug output: quantised zigzag levels in coding order, [picture][macroblock][6][64]
@@ -482,6 +567,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         chunk_bits[rec0] = (uint32_t)bits0;
         if (paired) chunk_bits[rec0 + g.chunks_per_slice] = (uint32_t)(real_bits - bits0);
     }
+    M1X_MARK(3);
 }
 
 // -------------------------------------------------------------------------------------------
@@ -824,7 +910,34 @@ cudaError_t m1k_launch_encode(const M1Geom &g, const M1Quant &q, const uint8_t *
     dim3 grid(g.chunks_per_slice, g.slices, n_frames);
     M1NzKeys nk;
     m1k_nz_keys(q, &nk);
+#ifdef M1_EXPERIMENTS
+    static const int stagger = m1x_env_int("M1_STAGGER_NS"), stagger_ctas = m1x_env_int("M1_STAGGER_CTAS") ? m1x_env_int("M1_STAGGER_CTAS") : M1_ENC_MIN_CTAS;
+    static const int trace_launch = m1x_env_int("M1_TRACE");    // n > 0: dump the timeline of the n-th launch to $M1_TRACE_FILE
+    static int launch_no = 0;
+    static unsigned long long *d_trace = nullptr;
+    ++launch_no;
+    const size_t n_ctas = (size_t)grid.x * grid.y * grid.z;
+    if (stagger) {
+        void *arr; cudaGetSymbolAddress(&arr, m1x_sm_arrivals);
+        cudaMemsetAsync(arr, 0, sizeof(unsigned int) * 1024, st);
+        if (launch_no == 1) { cudaMemcpyToSymbol(m1x_stagger_ns, &stagger, sizeof(int)); cudaMemcpyToSymbol(m1x_stagger_ctas, &stagger_ctas, sizeof(int)); }
+    }
+    if (trace_launch && launch_no == trace_launch) {
+        cudaMalloc(&d_trace, n_ctas * 32); cudaMemset(d_trace, 0, n_ctas * 32);
+        cudaMemcpyToSymbol(m1x_trace, &d_trace, sizeof(d_trace));
+    }
+#endif
     pick_encode_kernel(g, levels != nullptr)<<<grid, threads, smem, st>>>(g, nk, rgb, tables, staging, chunk_bits, levels, err);
+#ifdef M1_EXPERIMENTS
+    if (trace_launch && launch_no == trace_launch) {
+        cudaStreamSynchronize(st);
+        std::vector<unsigned long long> h(n_ctas * 4);
+        cudaMemcpy(h.data(), d_trace, n_ctas * 32, cudaMemcpyDeviceToHost);
+        unsigned long long *nul = nullptr; cudaMemcpyToSymbol(m1x_trace, &nul, sizeof(nul));
+        const char *fn = getenv("M1_TRACE_FILE");
+        if (FILE *f = fopen(fn ? fn : "gpurun_out/trace.bin", "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
+    }
+#endif
     return cudaGetLastError();
 }
 
