@@ -5,17 +5,9 @@
 #include "m1cu_block.cuh"
 #include "m1cu_colour.cuh"
 #include "m1cu_quant.h"
-#include <vector>
-#include <stdio.h>
 #ifdef M1_EXPERIMENTS
 #include "../../tools/experiments/m1x_env.h"
-// Profiling build only: per-CTA phase timeline (M1_TRACE) and a first-wave start stagger (M1_STAGGER_NS).
-__device__ unsigned long long *m1x_trace;       // [CTA][4]: (smid << 48 | start), end of colour, end of blocks, end   (globaltimer ns)
-__device__ unsigned int m1x_sm_arrivals[1024];  // CTAs that have started on each SM in this launch
-__device__ int m1x_stagger_ns, m1x_stagger_ctas;
-__device__ __forceinline__ unsigned long long m1x_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-__device__ __forceinline__ unsigned m1x_smid() { unsigned s; asm volatile("mov.u32 %0, %%smid;" : "=r"(s)); return s; }
-#define M1X_MARK(slot) do { if (m1x_trace && threadIdx.x == 0) m1x_trace[4 * m1x_lin + (slot)] = (m1x_now() & 0xffffffffffffull) | ((slot) == 0 ? (unsigned long long)m1x_smid() << 48 : 0ull); } while (0)
+#include "../../tools/experiments/m1x_trace.cuh"
 #else
 #define M1X_MARK(slot) do { } while (0)
 #endif
@@ -74,6 +66,16 @@ struct WindowWriter {
         if (lo && word + 1 >= 0 && word + 1 < nw) atomicOr(&win[word + 1], lo);
     }
 };
+
+// A block longer than 64 bits, or one that straddles the end of the window: coded again straight into the window.
+// Rare, and deliberately not inlined so that its set-up stays out of the kernel's common path.
+__device__ __noinline__ void recode_into_window(uint32_t *win, int my_off, int w0, int nw, bool first_of_mb, const short *rec,
+                                                int pb, unsigned long long nz, bool is_luma, const M1Tables *tb, int key)
+{
+    WindowWriter ww{win, my_off, w0, nw};
+    if (first_of_mb) ww.put(3u, 2);                         // address increment '1' + macroblock_type '1'
+    code_block(ww, rec, pb, nz, is_luma, tb, key);
+}
 
 // -------------------------------------------------------------------------------------------
 // Colour tiles.
@@ -480,10 +482,9 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     const int my_bits = acc.n;
     int incl = my_bits;
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += t;
-    }
+    for (int d = 1; d < 32; d <<= 1)                        // the shuffle's own predicate says "lane >= d"
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .s32 t;\n\tshfl.sync.up.b32 t|p, %0, %1, 0, 0xffffffff;\n\t@p add.s32 %0, %0, t;\n\t}"
+                     : "+r"(incl) : "r"(d));
     if (lane == 31) wtot[warp] = incl;
     const int t2 = 6 * T;                                    // first thread of the second record of a pair
     if (paired && tid == t2) wtot[8] = incl - my_bits;       // its exclusive prefix inside its warp
@@ -517,11 +518,13 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     const int total_bits = real_bits + gap;
     const int my_off = base + incl - my_bits + ((paired && tid >= t2) ? gap : 0);
 
-    const size_t rec0 = (size_t)frame * g.chunks_per_frame + (size_t)slice * g.chunks_per_slice + chunk;
-    uint32_t *out = staging + rec0 * (g.chunk_stride / 4);
+    // record index and word offsets in 32 bits: the staging of one launch round is bounded to 2 GiB (m1cu_create)
+    const unsigned rec0 = (unsigned)frame * (unsigned)g.chunks_per_frame + (unsigned)(slice * g.chunks_per_slice + chunk);
+    const unsigned rec_words = g.chunk_stride >> 2;
+    uint32_t *out = staging + (size_t)(rec0 * rec_words);
     // word v of the virtual bit string -> its place in the staging records
     const int vsplit = paired ? (bits0 + gap) >> 5 : 0x7fffffff;
-    uint32_t *out2 = staging + (rec0 + g.chunks_per_slice) * (g.chunk_stride / 4) - (paired ? vsplit : 0);
+    uint32_t *out2 = staging + (size_t)((rec0 + (unsigned)g.chunks_per_slice) * rec_words - (unsigned)(paired ? vsplit : 0));
     const int WW = g.win_words;                             // <= M1_WIN_WORDS (smaller only in tests)
     if (min(WW, (total_bits + 31) >> 5) + 2 > nthr) {       // uniform; rare at typical qualities
 #pragma unroll 1
@@ -530,10 +533,10 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     }
     for (int w0 = 0;; w0 += 32 * WW) {            // the window words in use are zero here
         if (tid == 0 && hdr_bits && w0 == 0) {
-            // source/mpeg1_blk.c:12-20: 000001 | (vertical_pos+1)&0xff | quant_scale(5)=1 | 0
-            WindowWriter ww{win, 0, 0, WW};
-            ww.put(1u, 24);
-            ww.put(((((uint32_t)(slice & 0xff) + 1u) & 0xffu) << 6) | (1u << 1), 14);
+            // source/mpeg1_blk.c:12-20: 000001 | (vertical_pos+1)&0xff | quant_scale(5)=1 | 0 = 38 bits at bit 0 of
+            // the chunk: word 0 = 0x000001 vv, word 1 starts 00001 0
+            atomicOr(&win[0], 0x100u | (((uint32_t)(slice & 0xff) + 1u) & 0xffu));
+            atomicOr(&win[1], 0x08000000u);
         }
         if (active && my_off < w0 + 32 * WW && my_off + my_bits > w0) {
             if (my_bits <= 64 && my_off >= w0 && my_off + my_bits <= w0 + 32 * WW) {
@@ -545,9 +548,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                 if (b) atomicOr(&win[word + 1], b);
                 if (c) atomicOr(&win[word + 2], c);
             } else {
-                WindowWriter ww{win, my_off, w0, WW};           // long block, or one straddling the window
-                if (blk == 0) ww.put(3u, 2);
-                code_block(ww, rec, pb, nz, is_luma, tb, tid & 7);
+                recode_into_window(win, my_off, w0, WW, blk == 0, rec, pb, nz, is_luma, tb, tid & 7);
             }
         }
         __syncthreads();
@@ -911,32 +912,11 @@ cudaError_t m1k_launch_encode(const M1Geom &g, const M1Quant &q, const uint8_t *
     M1NzKeys nk;
     m1k_nz_keys(q, &nk);
 #ifdef M1_EXPERIMENTS
-    static const int stagger = m1x_env_int("M1_STAGGER_NS"), stagger_ctas = m1x_env_int("M1_STAGGER_CTAS") ? m1x_env_int("M1_STAGGER_CTAS") : M1_ENC_MIN_CTAS;
-    static const int trace_launch = m1x_env_int("M1_TRACE");    // n > 0: dump the timeline of the n-th launch to $M1_TRACE_FILE
-    static int launch_no = 0;
-    static unsigned long long *d_trace = nullptr;
-    ++launch_no;
-    const size_t n_ctas = (size_t)grid.x * grid.y * grid.z;
-    if (stagger) {
-        void *arr; cudaGetSymbolAddress(&arr, m1x_sm_arrivals);
-        cudaMemsetAsync(arr, 0, sizeof(unsigned int) * 1024, st);
-        if (launch_no == 1) { cudaMemcpyToSymbol(m1x_stagger_ns, &stagger, sizeof(int)); cudaMemcpyToSymbol(m1x_stagger_ctas, &stagger_ctas, sizeof(int)); }
-    }
-    if (trace_launch && launch_no == trace_launch) {
-        cudaMalloc(&d_trace, n_ctas * 32); cudaMemset(d_trace, 0, n_ctas * 32);
-        cudaMemcpyToSymbol(m1x_trace, &d_trace, sizeof(d_trace));
-    }
+    m1x_before_launch(grid, st);
 #endif
     pick_encode_kernel(g, levels != nullptr)<<<grid, threads, smem, st>>>(g, nk, rgb, tables, staging, chunk_bits, levels, err);
 #ifdef M1_EXPERIMENTS
-    if (trace_launch && launch_no == trace_launch) {
-        cudaStreamSynchronize(st);
-        std::vector<unsigned long long> h(n_ctas * 4);
-        cudaMemcpy(h.data(), d_trace, n_ctas * 32, cudaMemcpyDeviceToHost);
-        unsigned long long *nul = nullptr; cudaMemcpyToSymbol(m1x_trace, &nul, sizeof(nul));
-        const char *fn = getenv("M1_TRACE_FILE");
-        if (FILE *f = fopen(fn ? fn : "gpurun_out/trace.bin", "wb")) { fwrite(h.data(), 8, h.size(), f); fclose(f); }
-    }
+    m1x_after_launch(grid, st);
 #endif
     return cudaGetLastError();
 }
