@@ -355,6 +355,12 @@ int m1cu_encode_device(m1cu_ctx *ctx, const uint8_t *d_rgb, int n_frames, uint8_
     CU(cudaMemsetAsync(ctx->d_running, 0, sizeof(unsigned long long), st));
     int bx = (g.chunks_per_frame + 7) / 8;                     // k_stitch: one warp per chunk, 8 warps per CTA
     if (bx > 512) bx = 512;
+    {   // many pictures per launch: cap the grid at 32 CTAs per SM and let every warp loop over chunks (20 400 CTAs of
+        // one chunk per warp for 300 pictures of 1080p are bound by CTA launches: 51.5 -> 47.2 us, profiles/r2_stitch_grid.txt)
+        const int nb0 = n_frames < ctx->batch_frames ? n_frames : ctx->batch_frames;
+        const int want = (148 * 32 + nb0 - 1) / nb0;
+        if (want < bx) bx = want;
+    }
     const int rounds = (n_frames + ctx->batch_frames - 1) / ctx->batch_frames;
     // More than one launch round (the staging memory is bounded): the layout + stitch of round r run on a side
     // stream beside the chunk encoder of round r + 1, with two sets of staging / chunk arrays.  Everything is
