@@ -44,6 +44,15 @@ M1_HD uint32_t m1_funnel_l(uint32_t lo, uint32_t hi, uint32_t s)   // high word 
     return s ? (hi << s) | (lo >> (32 - s)) : hi;
 #endif
 }
+// lo | hi << 16 for two values below 2^16 as ONE byte permute (the compiler cannot know the range and would shift + or)
+M1_HD uint32_t m1_pack16(uint32_t lo, uint32_t hi)
+{
+#ifdef __CUDA_ARCH__
+    return __byte_perm(lo, hi, 0x5410);
+#else
+    return (lo & 0xffffu) | (hi << 16);
+#endif
+}
 // a + b + c and a + b - c as ONE IADD3 each.  Written as two PTX adds with a private temporary: in C
 // the compiler would share (a + b) between the sum and the difference and spend three instructions
 // on the pair instead of two.
@@ -195,7 +204,7 @@ M1_HD unsigned long long pack_and_flag(const int (&v)[64], uint32_t (&pk)[32], c
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
             const int w = hblk * 16 + i, z = hblk * 32 + i;
-            const uint32_t p = (uint32_t)v[zz_raster(z)] | ((uint32_t)v[zz_raster(z + 16)] << 16);
+            const uint32_t p = m1_pack16((uint32_t)v[zz_raster(z)], (uint32_t)v[zz_raster(z + 16)]);
             pk[w] = p;
             const uint32_t f = ((p + nk.ka[w]) | (nk.kb[w] - p)) & 0x80008000u;
             fl = f + (fl >> 1);

@@ -321,11 +321,14 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     // warp's 32 strips hold 256 quads; 4 queues = the window's 512 words), counted in wtot[4 + warp].
     // Queue and counter are private to the warp until the barrier, so zeroing the counter needs no
     // CTA-wide barrier of its own.
+#if M1_COLOUR_SPLIT != 2
     unsigned short *fixq = (unsigned short *)win + 256 * (tid >> 5);
     int *fix_cnt = wtot + 4 + (tid >> 5);
-    if ((tid & 31) == 0) { wtot[tid >> 5] = 0; *fix_cnt = 0; }
-    if (tid < 4 && tid >= (nthr >> 5)) { wtot[tid] = 0; wtot[4 + tid] = 0; }   // warps this CTA does not have
+    if ((tid & 31) == 0) *fix_cnt = 0;
+    if (tid < 4 && tid >= (nthr >> 5)) wtot[4 + tid] = 0;
     __syncwarp();
+#endif
+    if (tid < 4 && tid >= (nthr >> 5)) wtot[tid] = 0;           // bit totals of the warps this CTA does not have (the others write theirs)
 
     const uint8_t *fr = rgb + (size_t)frame * g.frame_stride;
 
