@@ -573,10 +573,10 @@ def run_ours(args):
                          "algorithmic_bytes_per_frame": head["alg_bytes_per_frame"], "frames_per_launch": head["frames_per_launch"],
                          "launch_ms": head["launch_ms"], "whole_step_frac": head["whole_step_frac"],
                          "note": ("the dominant kernel is instruction-issue bound, not HBM bound: the reference's exact double-precision "
-                                  "colour chain + int32 DCT + VLC cost about 60 issue slots per pixel, issued at 0.75 per cycle and "
-                                  "sub-partition (two-cycle FP64 / ALU / IMAD instructions), DRAM at 16 % of peak; an integer colour path, "
-                                  "a mixed one and a barrier-free warp-per-chunk kernel were built, are bit-exact and measured slower "
-                                  "(DESIGN.md section 7, profiles/r2_*)"),
+                                  "colour chain + int32 DCT + VLC cost 59 issue slots per pixel, issued at 0.77 per cycle and "
+                                  "sub-partition (two-cycle FP64 / ALU / IMAD instructions), DRAM at 17 % of peak; an integer colour path, "
+                                  "a mixed one, a barrier-free warp-per-chunk kernel and a queue-fed persistent form were built, are "
+                                  "bit-exact and measured slower (DESIGN.md section 7, profiles/r2_*)"),
                          "kernel_ms_per_step": head["kernel_ms_per_step"]},
         }
         line["memcheck"] = ("compute-sanitizer is closed on this pool: no memcheck / racecheck run of the kernels exists; evidence is the "
