@@ -39,6 +39,8 @@ struct M1Geom {
                                // ONE CTA encodes the last chunks of slices 2k and 2k+1 together (FULL mode only)
     unsigned inv_nbc[3];       // ceil(2^16 / block columns) of a full chunk [0], of a slice's last chunk [1] and of a
                                // pair of last chunks [2]: x / nbc == (x * inv) >> 16 for x < 2048
+    int flat_range;            // >= 0: a block whose samples span at most this much has no non-zero AC level at this quality
+                               // (m1_flat_range, m1cu_quant.h) and skips DCT + quantiser test; -1: no such range
     unsigned chunk_stride;     // staging bytes per chunk (multiple of 16)
     unsigned long long frame_stride;   // input bytes per picture
 };

@@ -308,7 +308,8 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     short *rec = (short *)smem;                                  // aliases planes (see layout note)
     uint32_t *win = (uint32_t *)(planes + 6 * C * 64);           // [M1_WIN_WORDS + 4]
     M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS + 4);         // 16-byte aligned
-    int *wtot = (int *)(tb + 1);                                 // [12]: [0..3] bits per warp, [4..7] fix-up queue lengths, [8] pair split; 16-byte aligned
+    int *wtot = (int *)(tb + 1);                                 // [48]: [0..3] bits per warp, [4..7] fix-up queue lengths, [8] pair split,
+                                                                 // [9] blocks queued for the DCT, [16..47] their indices (bytes); 16-byte aligned
 
     // Per-CTA prologue, kept short: the coder's tables up to zofs[] in 128-bit pieces (the non-zero
     // keys come from the constant bank), and only the first blockDim.x window words zeroed -- a chunk
@@ -329,6 +330,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     __syncwarp();
 #endif
     if (tid < 4 && tid >= (nthr >> 5)) wtot[tid] = 0;           // bit totals of the warps this CTA does not have (the others write theirs)
+    if (tid == 0) wtot[9] = 0;                                  // blocks queued for the DCT (phase 2b)
 
     const uint8_t *fr = rgb + (size_t)frame * g.frame_stride;
 
@@ -444,36 +446,100 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
 
     // ---- phase 2: one thread per 8x8 block, threads in CODING order (t = 6*mb + blk), so the
     // bit offsets are a plain scan over the thread index.  pb = the thread's plane block.
+    //   2a  every block thread reads its block once for min / max / sum.  A block whose samples span at most
+    //       g.flat_range cannot have a non-zero AC level at this quality (m1_flat_range, m1cu_quant.h): its DC
+    //       coefficient is (sum + 16) >> 3 and it is done.  The others are queued.
+    //   2b  the queued blocks are transformed and tested by ALL threads of the CTA, one block per thread (the fourth
+    //       warp, which owns no block, takes its share): the cost follows the number of blocks that need a DCT,
+    //       not the number of warps that contain one.
+    //   3   every block thread codes its own block from its record and non-zero mask.
     const int mb = tid / 6, blk = tid - mb * 6;             // macroblock in chunk, block 0..5
     const bool active = mb < nmb;
     const bool is_luma = blk < 4;
     const int pb = is_luma ? (blk >> 1) * 2 * C + 2 * mb + (blk & 1) : blk * C + mb;
+    const int lane = tid & 31, warp = tid >> 5;
     unsigned long long nz = 0;
     BitAcc acc{0u, 0u, 0};
-    if (active) {
-        int v[64];
-        {
+    unsigned char *todo = (unsigned char *)(wtot + 16);      // [128] coding-order indices of the blocks that need a DCT
+    bool queued = active;
+    if (g.flat_range >= 0) {
+        const unsigned amask = __ballot_sync(0xffffffffu, active);
+        if (active) {
             const int key4 = (tid & 7) << 2;                 // == blk_key(pb, C): threads are in coding order
             const int *src = planes + pb * 64;
+            int mn = 255, mx = 0, sum = 0;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int o = ((i << 2) ^ key4);
                 const int4 a = *(const int4 *)(src + o);
                 const int4 b = *(const int4 *)(src + o + 32);
-                v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
-                v[32 + 4 * i] = b.x; v[32 + 4 * i + 1] = b.y; v[32 + 4 * i + 2] = b.z; v[32 + 4 * i + 3] = b.w;
+                mn = __vimin3_s32(mn, a.x, a.y); mn = __vimin3_s32(mn, a.z, a.w); mn = __vimin3_s32(mn, b.x, b.y); mn = __vimin3_s32(mn, b.z, b.w);
+                mx = __vimax3_s32(mx, a.x, a.y); mx = __vimax3_s32(mx, a.z, a.w); mx = __vimax3_s32(mx, b.x, b.y); mx = __vimax3_s32(mx, b.z, b.w);
+                sum = m1_add3(sum, a.x, a.y); sum = m1_add3(sum, a.z, a.w); sum = m1_add3(sum, b.x, b.y); sum = m1_add3(sum, b.z, b.w);
+                // busy content: stop reading as soon as no block of this warp can pass any more
+                if ((i == 1 || i == 3) && __all_sync(amask, mx - mn > g.flat_range)) break;
+            }
+            if (mx - mn <= g.flat_range) {
+                queued = false;
+                // source/image_processing.c:296: dct[0][0] = (x6 + 16) >> 3, x6 = sum of the eight row sums
+                const int dcb = (sum + (16 + (M1_COEF_BIAS << 3))) >> 3;
+                const int m0 = 0x7800 - (int)(nk.ka[0] & 0xffffu), c = dcb - M1_COEF_BIAS;
+                nz = (c >= m0 || c <= -m0) ? 1ull : 0ull;
+                if (kLevels) {                               // the level dump reads every position of the record
+#pragma unroll
+                    for (int gI = 0; gI < 8; ++gI)
+                        *(uint4 *)(rec + pb * 128 + (gI << 3)) = make_uint4(0x08000800u, 0x08000800u, 0x08000800u, 0x08000800u);
+                }
+                rec[rec_index(pb, 0, tid & 7)] = (short)dcb;
             }
         }
-        fdct8x8(v);
-        // packed coefficient pairs + the zigzag-order non-zero mask (m1cu_block.cuh)
-        uint32_t pk[32];
-        nz = pack_and_flag(v, pk, nk);
-        // the block's samples are in registers now: its 256 bytes of plane become the record
+    }
+    {   // queue: warp-aggregated slot allocation
+        const unsigned qmask = __ballot_sync(0xffffffffu, queued);
+        if (qmask) {
+            int base = 0;
+            const int leader = __ffs(qmask) - 1;
+            if (lane == leader) base = atomicAdd(wtot + 9, __popc(qmask));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (queued) todo[base + __popc(qmask & ((1u << lane) - 1u))] = (unsigned char)tid;
+        }
+    }
+    __syncthreads();
+    {
+        const int n_todo = wtot[9];
+#pragma unroll 1
+        for (int i = tid; i < n_todo; i += nthr) {
+            const int t = todo[i], m2 = t / 6, b2 = t - m2 * 6;
+            const int pb2 = b2 < 4 ? (b2 >> 1) * 2 * C + 2 * m2 + (b2 & 1) : b2 * C + m2;
+            int v[64];
+            {
+                const int key4 = (t & 7) << 2;
+                const int *src = planes + pb2 * 64;
 #pragma unroll
-        for (int gI = 0; gI < 8; ++gI)
-            *(uint4 *)(rec + pb * 128 + (((gI ^ tid) & 7) << 3)) =
-                make_uint4(pk[4 * gI], pk[4 * gI + 1], pk[4 * gI + 2], pk[4 * gI + 3]);
-
+                for (int k = 0; k < 8; ++k) {
+                    const int o = ((k << 2) ^ key4);
+                    const int4 a = *(const int4 *)(src + o);
+                    const int4 b = *(const int4 *)(src + o + 32);
+                    v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = a.z; v[4 * k + 3] = a.w;
+                    v[32 + 4 * k] = b.x; v[32 + 4 * k + 1] = b.y; v[32 + 4 * k + 2] = b.z; v[32 + 4 * k + 3] = b.w;
+                }
+            }
+            fdct8x8(v);
+            // packed coefficient pairs + the zigzag-order non-zero mask (m1cu_block.cuh)
+            uint32_t pk[32];
+            const unsigned long long nz2 = pack_and_flag(v, pk, nk);
+            // the block's samples are in registers now: the first half of its 256 bytes of plane becomes the record,
+            // the first eight bytes of the second half carry the mask to the block's own thread
+#pragma unroll
+            for (int gI = 0; gI < 8; ++gI)
+                *(uint4 *)(rec + pb2 * 128 + (((gI ^ t) & 7) << 3)) =
+                    make_uint4(pk[4 * gI], pk[4 * gI + 1], pk[4 * gI + 2], pk[4 * gI + 3]);
+            *(unsigned long long *)(planes + pb2 * 64 + 32) = nz2;
+        }
+    }
+    __syncthreads();
+    if (active) {
+        if (queued) nz = *(const unsigned long long *)(planes + pb * 64 + 32);
         // ---- phase 3: code the block into registers ------------------------------------------
         if (blk == 0) { acc.lo = 3u; acc.n = 2; }           // address increment '1' + macroblock_type '1'
         if (code_block(acc, rec, pb, nz, is_luma, tb, tid & 7)) atomicOr(err, M1_ERRBIT_LEVEL);
@@ -481,7 +547,6 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     }
 
     // scan of the block lengths in thread (= coding) order
-    const int lane = tid & 31, warp = tid >> 5;
     const int my_bits = acc.n;
     int incl = my_bits;
 #pragma unroll
@@ -874,7 +939,7 @@ size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
 #else
     const size_t pad = 0;
 #endif
-    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 4) * 4 + sizeof(M1Tables) + 12 * sizeof(int) + 16 + pad;
+    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 4) * 4 + sizeof(M1Tables) + 48 * sizeof(int) + 16 + pad;
 }
 
 int m1k_encode_threads(const M1Geom &g) { return (8 * g.chunk_mbs + 31) & ~31; }   // one colour tile per thread; 6C of them own a block

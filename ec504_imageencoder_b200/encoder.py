@@ -67,7 +67,7 @@ class M1Encoder:
     def __init__(self, width: int, height: int, channels: int = 3, mode: int = MODE_FULL,
                  quality: int = DEFAULT_QUALITY, max_frames: int = 64, device: int | None = None,
                  chunk_mbs: int = 0, chunk_even: bool = False, win_words: int = 0, no_tail_pairing: bool = False,
-                 batch_frames: int = 0):
+                 batch_frames: int = 0, no_flat_skip: bool = False):
         self.lib = _native.m1cu()
         if self.lib.m1cu_device_count() == 0 or not torch.cuda.is_available():
             raise M1Error(-2, "no CUDA device: the encode path has no CPU fallback")
@@ -76,7 +76,8 @@ class M1Encoder:
         self.mode, self.quality, self.max_frames = int(mode), int(quality), int(max_frames)
         h = C.c_void_p()
         # work-partition knobs (m1cu_tuning; tests and sweeps only, no effect on the bytes)
-        tuning = (C.c_int * 5)(int(chunk_mbs), int(bool(chunk_even)), int(win_words), int(bool(no_tail_pairing)), int(batch_frames))
+        tuning = (C.c_int * 6)(int(chunk_mbs), int(bool(chunk_even)), int(win_words), int(bool(no_tail_pairing)), int(batch_frames),
+                               int(bool(no_flat_skip)))
         rc = self.lib.m1cu_create_ex(C.byref(h), self.device, self.width, self.height, self.channels,
                                      self.mode, self.quality, self.max_frames, tuning)
         if rc != 0:

@@ -88,6 +88,9 @@ typedef struct m1cu_tuning {
     int batch_frames;/* pictures per launch round, > 0 lowers the default (about 2 GiB of staging); a call
                         with more pictures runs several rounds, layout + stitch of one beside the encode
                         of the next                                                                     */
+    int no_flat_skip;/* != 0: every block goes through DCT + quantiser test (default: a block whose samples span
+                        so little that no AC level can be non-zero at this quality -- a rigorous bound, see
+                        csrc/m1cu_quant.h -- only gets its DC coefficient computed)                            */
 } m1cu_tuning;
 int  m1cu_create_ex(m1cu_ctx **out, int device, int width, int height, int channels,
                     int mode, int quality_factor, int max_frames, const m1cu_tuning *tuning);

@@ -140,4 +140,19 @@ void m1bh_ycbcr_exact(const unsigned char *rgb, long n, unsigned char *y, unsign
     }
 }
 
+// The flat-block bound of m1cu_quant.h: largest sample span for which no AC level can be non-zero (-1: none), and the
+// L1 norms of the row- / column-pass functionals it is built from.
+int m1bh_flat_range(const int32_t qm[64]) { return m1_flat_range(qm); }
+void m1bh_l1_norms(double a_row[8], double a_col[8]) { m1_fdct_l1_norms(a_row, a_col); }
+// the real-valued (truncation-free) 2-D transform of a block: out[u*8+v]
+void m1bh_fdct_linear(const double samples[64], double out[64])
+{
+    double rows[64], col[8], r[8];
+    for (int i = 0; i < 8; ++i) m1_fdct_linear_1d(samples + 8 * i, rows + 8 * i, false);
+    for (int j = 0; j < 8; ++j) {
+        for (int i = 0; i < 8; ++i) col[i] = rows[8 * i + j];
+        m1_fdct_linear_1d(col, r, true);
+        for (int u = 0; u < 8; ++u) out[8 * u + j] = r[u];
+    }
+}
 }  // extern "C"

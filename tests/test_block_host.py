@@ -121,6 +121,79 @@ def test_block_functions_match_oracle(bh, port, quality):
             assert acc == ref_bits, f"register accumulator differs on block {i}"
 
 
+def test_flat_block_bound(bh, port):
+    """The flat-block shortcut of k_encode_chunks (m1_flat_range, csrc/m1cu_quant.h): a block whose samples span at most R
+    has no non-zero AC level and its DC coefficient is (sum + 16) >> 3.  Checked against the oracle's fast_DCT
+    (source/image_processing.c:192-307) and truncating quantiser (:349-370) for every quality factor with
+    (a) the extremal blocks of every AC position -- samples at the two ends of the span, signs = the signs of that
+        position's linear functional and their negation --, (b) random two-level blocks, (c) uniform random blocks;
+    and the truncation-error term of the bound on unrestricted random blocks."""
+    bh.m1bh_flat_range.restype = C.c_int
+    bh.m1bh_flat_range.argtypes = [C.c_void_p]
+    a_row, a_col = np.zeros(8), np.zeros(8)
+    bh.m1bh_l1_norms(a_row.ctypes.data_as(C.c_void_p), a_col.ctypes.data_as(C.c_void_p))
+    lin = np.zeros(64)
+
+    def linear(block):
+        b = np.ascontiguousarray(block, np.float64).reshape(64)
+        bh.m1bh_fdct_linear(b.ctypes.data_as(C.c_void_p), lin.ctypes.data_as(C.c_void_p))
+        return lin.reshape(8, 8).copy()
+
+    # signs of every position's functional: response to unit impulses
+    signs = np.zeros((8, 8, 64))
+    for k in range(64):
+        e = np.zeros(64); e[k] = 1.0
+        signs[:, :, k] = np.sign(linear(e))
+    rng = np.random.default_rng(2024)
+    # (1) truncations: |fast_DCT - linear| <= A_col(u) + 2.05 at every AC position, on any block
+    for blk in blocks(rng, 600):
+        ref = np.asarray(port.fdct8x8(blk)).reshape(8, 8).astype(np.float64)
+        err = np.abs(ref - linear(blk.astype(np.float64)))
+        err[0, 0] = 0
+        assert (err <= a_col[:, None] + 2.05).all(), err.max()
+    # (2) the range itself
+    seen = set()
+    for q in range(-2, 104):
+        qm = port.qmatrix(q)
+        R = bh.m1bh_flat_range(qm.ctypes.data)
+        key = (R, tuple(qm.tolist()))
+        if key in seen:
+            continue
+        seen.add(key)
+        m = qm.reshape(8, 8).astype(np.float64)
+        if R < 0:
+            continue
+        assert R % 2 == 0 and R <= 255
+        # the bound it was derived from really holds with margin, and R + 2 would violate it somewhere
+        W = a_col[:, None] * a_row[None, :]
+        room = m - (a_col[:, None] + 2.05) - (R // 2) * W
+        room[0, 0] = 1
+        assert (room > 0).all()
+        room2 = m - (a_col[:, None] + 2.05) - (R // 2 + 1) * W
+        room2[0, 0] = 1
+        assert (room2 <= 0).any()
+        cases = []
+        for lo in sorted({0, 255 - R, (255 - R) // 2, int(rng.integers(0, 256 - R))}):
+            for u in range(8):
+                for v in range(8):
+                    if u == 0 and v == 0:
+                        continue
+                    s = signs[u, v]
+                    cases.append(np.where(s > 0, lo + R, lo))
+                    cases.append(np.where(s > 0, lo, lo + R))
+            for _ in range(40):
+                cases.append(np.where(rng.integers(0, 2, 64) > 0, lo + R, lo))
+                cases.append(lo + rng.integers(0, R + 1, 64))
+        for blk in cases:
+            blk = blk.astype(np.uint8)
+            assert int(blk.max()) - int(blk.min()) <= R
+            ref = np.asarray(port.fdct8x8(blk)).reshape(64)
+            zz = port.quant_zigzag(ref, qm)
+            assert not zz[1:].any(), (q, R, blk.reshape(8, 8), zz)
+            assert ref[0] == (int(blk.astype(np.int64).sum()) + 16) >> 3
+    assert bh.m1bh_flat_range(port.qmatrix(12).ctypes.data) == 16
+
+
 def test_quantiser_reciprocals_every_quality(bh, port):
     """m1_make_quant's exhaustive self-check (|c| <= 2047) passes for every quality factor."""
     for q in range(1, 101):

@@ -23,7 +23,8 @@ CASES = ((352, 240, 3, 12, 0), (1920, 1080, 2, 12, 0), (640, 480, 2, 50, 1), (19
                                     {"win_words": 8}, {"win_words": 5, "chunk_mbs": 3}, {"win_words": 6, "chunk_mbs": 5},
                                     {"batch_frames": 1}, {"batch_frames": 2, "chunk_mbs": 5},
                                     {"no_tail_pairing": True}, {"no_tail_pairing": True, "win_words": 8},
-                                    {"chunk_mbs": 14}, {"chunk_mbs": 14, "win_words": 4}, {"chunk_mbs": 9, "win_words": 7}])
+                                    {"chunk_mbs": 14}, {"chunk_mbs": 14, "win_words": 4}, {"chunk_mbs": 9, "win_words": 7},
+                                    {"no_flat_skip": True}, {"no_flat_skip": True, "chunk_mbs": 5, "win_words": 6}])
 def test_kernel_variant(tuning, port):
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
@@ -38,6 +39,43 @@ def test_kernel_variant(tuning, port):
             rp, rl = port.encode_picture(host[f], q, 0, want_levels=True)
             assert np.array_equal(lev[f], rl), (W, H, f)
             assert pay[f] == rp and pay2[f] == rp, (W, H, f)
+        enc.close()
+
+
+@pytest.mark.parametrize("quality", [5, 12, 20, 50, 89])
+def test_flat_block_skip_at_the_boundary(port, quality):
+    """Blocks whose samples span at most m1_flat_range(quality) skip the DCT (only their DC coefficient is computed, the
+    others are queued and transformed by the whole CTA).  Pictures whose 8x8 blocks span R - 3 .. R + 3 grey levels around
+    random bases (so passes and failures mix inside every warp, and whole macroblocks of each kind occur), plus colour
+    noise of the same amplitudes: levels and bytes against the oracle, with and without the shortcut."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from ec504_imageencoder_b200 import M1Encoder
+    R = {5: 42, 12: 16, 20: 10, 50: 2, 89: 0}[quality]
+    W, H, n = 640, 368, 4
+    rng = np.random.default_rng(quality)
+    frames = np.zeros((n, H, W, 3), np.uint8)
+    for f in range(n):
+        by, bx = H // 8, W // 8
+        span = rng.integers(max(R - 3, 0), R + 4, (by, bx))
+        if f == 1:
+            span = np.repeat(np.repeat(rng.integers(max(R - 3, 0), R + 4, (by // 2, bx // 2)), 2, 0), 2, 1)   # per macroblock
+        base = rng.integers(0, 256 - (R + 4), (by, bx))
+        px = base.repeat(8, 0).repeat(8, 1) + (rng.random((H, W)) * (span.repeat(8, 0).repeat(8, 1) + 1)).astype(np.int64)
+        if f < 2:
+            frames[f] = px[:, :, None]                                             # grey: Y ~ the pattern, chroma flat
+        else:
+            frames[f] = np.clip(px[:, :, None] + rng.integers(0, R // 2 + 2, (H, W, 3)), 0, 255)
+    want = [port.encode_picture(frames[f], quality, 0, want_levels=True) for f in range(n)]
+    for nfs in (False, True):
+        enc = M1Encoder(W, H, 3, 0, quality, max_frames=n, no_flat_skip=nfs)
+        rgb = torch.from_numpy(frames).cuda()
+        res = enc.encode_device(rgb, want_levels=True)
+        res2 = enc.encode_device(rgb)
+        pay, pay2, lev = res.payloads(), res2.payloads(), res.levels.cpu().numpy()
+        for f in range(n):
+            assert np.array_equal(lev[f], want[f][1]), (quality, nfs, f)
+            assert pay[f] == want[f][0] and pay2[f] == want[f][0], (quality, nfs, f)
         enc.close()
 
 
