@@ -361,6 +361,7 @@ class Bench:
             "parity": {"frames_checked": checked, "identical": identical, "ties": 0,
                        "pct_identical": 100.0 * identical / max(1, checked), "checker": parity["checker"],
                        "what": "quantised zigzag levels and payload bytes of the first and last frame each rank timed"},
+            "flat_blocks": parity.get("flat"),
             "enc": enc, "rgb": rgb,
         }
         if pg is not None:
@@ -418,7 +419,30 @@ class Bench:
                 same = np.array_equal(small.levels[j].cpu().numpy(), want_lev) and pays[j] == want_pay and timed == want_pay
                 identical += bool(same)
         return {"frames_checked": len(idx), "identical": identical,
-                "checker": "unmodified reference functions (oracle/_ref, -O2)" if use_ref else "oracle C port"}
+                "checker": "unmodified reference functions (oracle/_ref, -O2)" if use_ref else "oracle C port",
+                "flat": self._flat_share(enc, rgb[idx[0]].cpu().numpy() if idx else None)}
+
+    @staticmethod
+    def _flat_share(enc, host):
+        """Share of the first timed frame's 8x8 blocks whose samples span at most m1cu_flat_range (those skip the DCT in
+        k_encode_chunks): computed on the host from the oracle's planes, outside every timed region."""
+        import numpy as np
+        import oracle
+        R = int(getattr(enc, "flat_range", -1))
+        if host is None or R < 0:
+            return {"range": R, "blocks_skipping_dct_pct": 0.0}
+        port = oracle.Port()
+        H, W = host.shape[:2]
+        planes = [np.asarray(p).reshape(H, W).astype(np.int32) for p in port.rgb_to_ycbcr(host)]
+        pad = lambda p: np.pad(p, ((0, (-p.shape[0]) % 16), (0, (-p.shape[1]) % 16)), mode="edge")
+        y, cb, cr = (pad(p) for p in planes)
+        sub = lambda p: (p[0::2, 0::2] + p[0::2, 1::2] + p[1::2, 0::2] + p[1::2, 1::2]) // 4
+
+        def spans(p):
+            b = p.reshape(p.shape[0] // 8, 8, p.shape[1] // 8, 8)
+            return (b.max(axis=(1, 3)) - b.min(axis=(1, 3))).ravel()
+        sp = np.concatenate([spans(y), spans(sub(cb)), spans(sub(cr))])
+        return {"range": R, "blocks_skipping_dct_pct": round(100.0 * float((sp <= R).mean()), 2)}
 
     # -- e2e through the host-buffer C-ABI call ------------------------------------------------------
     def e2e(self, enc, rgb, n):
@@ -551,6 +575,11 @@ def run_ours(args):
             "payload_bytes_per_frame": head["payload_bytes_per_frame"],
             "clocks": head["clocks"],
             "parity": head["parity"],
+            "flat_blocks": dict(head.get("flat_blocks") or {}, note=(
+                "k_encode_chunks computes only the DC coefficient of a block whose samples span at most `range` grey levels: a "
+                "rigorous bound (csrc/m1cu_quant.h, tests/test_block_host.py::test_flat_block_bound) proves every AC level of such "
+                "a block zero at this quality; throughput therefore depends on content -- see the noise rows of other_configs, "
+                "where no block qualifies; rank 0's first timed frame")),
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h,
                     "frames_per_gpu_per_step": n_e2e,
                     "timer": "host wall clock around m1cu_encode_host (pinned input, pageable output), max over ranks",
@@ -606,7 +635,7 @@ def _other(name, w, h, q, r):
          "payload_bytes_per_frame": r["payload_bytes_per_frame"],
          "roofline": {"kernel": "k_encode_chunks", "frac": r["frac"], "achieved": r["achieved_gbs"], "launch_ms": r["launch_ms"],
                       "frames_per_launch": r["frames_per_launch"], "whole_step_frac": r["whole_step_frac"]},
-         "parity": r["parity"]}
+         "parity": r["parity"], "flat_blocks": r.get("flat_blocks")}
     if r["gather"] is not None:
         o["gather_verified"] = r["gather"]["gather_verified"]
         o["ranks"] = r["gather"]["ranks"]

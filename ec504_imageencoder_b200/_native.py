@@ -84,6 +84,7 @@ def m1cu() -> C.CDLL:
         "m1cu_set_stream": (C.c_int, [vp, vp]),
         "m1cu_synchronize": (C.c_int, [vp]),
         "m1cu_macroblocks_per_frame": (C.c_int, [vp]),
+        "m1cu_flat_range": (C.c_int, [vp]),
         "m1cu_frame_bytes_in": (C.c_size_t, [vp]),
         "m1cu_payload_bound": (C.c_size_t, [vp]),
         "m1cu_typical_out_bytes": (C.c_size_t, [vp, C.c_int]),
@@ -120,7 +121,7 @@ def m1cu() -> C.CDLL:
 
 M1CU_SYMBOLS = (
     "m1cu_abi_version", "m1cu_device_count", "m1cu_qmatrix", "m1cu_last_error", "m1cu_create", "m1cu_create_ex",
-    "m1cu_destroy", "m1cu_set_stream", "m1cu_synchronize", "m1cu_macroblocks_per_frame",
+    "m1cu_destroy", "m1cu_set_stream", "m1cu_synchronize", "m1cu_macroblocks_per_frame", "m1cu_flat_range",
     "m1cu_frame_bytes_in", "m1cu_payload_bound", "m1cu_typical_out_bytes", "m1cu_encode_device",
     "m1cu_check", "m1cu_encode_host", "m1cu_ycbcr_planes", "m1cu_host_batch_planes", "m1cu_synth_rgb", "m1cu_launch_count",
     "m1cu_enable_timing", "m1cu_kernel_times",

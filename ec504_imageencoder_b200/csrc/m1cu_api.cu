@@ -324,6 +324,7 @@ int m1cu_synchronize(m1cu_ctx *ctx)
 }
 
 int m1cu_macroblocks_per_frame(const m1cu_ctx *ctx) { return ctx ? ctx->g.mbs_per_frame : 0; }
+int m1cu_flat_range(const m1cu_ctx *ctx) { return ctx ? ctx->g.flat_range : -1; }
 size_t m1cu_frame_bytes_in(const m1cu_ctx *ctx) { return ctx ? (size_t)ctx->g.frame_stride : 0; }
 
 size_t m1cu_payload_bound(const m1cu_ctx *ctx)

@@ -124,35 +124,51 @@ M1_HD Fdct8 fdct_core(int x0, int x1, int x2, int x3, int x4, int x5, int x6, in
 // adds into the IMAD.HI's 64-bit addend and pays three moves per fold; the column pass's last
 // multiply-shift as IMAD.WIDE -- register pairs cost more moves than the shifts they save.)
 #define M1_COEF_BIAS 2048
-M1_HD void fdct8x8(int (&v)[64])
+// One row of the row pass: x0..x7 in, the eight row-pass outputs out[0..7] (source/image_processing.c:198-250).
+M1_HD void fdct_row(int x0, int x1, int x2, int x3, int x4, int x5, int x6, int x7, int (&out)[8])
 {
     const int r2 = 181;
+    Fdct8 o = fdct_core(x0, x1, x2, x3, x4, x5, x6, x7);
+    out[0] = o.t0;
+    out[4] = o.t1;
+    out[2] = o.t2 >> 10;
+    out[6] = o.t3 >> 10;
+    out[7] = m1_addsub3(o.p3, o.p1, o.t5) >> 10;
+    out[1] = m1_add3(o.p3, o.p1, o.t5) >> 10;
+    out[3] = (o.t6 * r2) >> 17;
+    out[5] = (o.t7 * r2) >> 17;
+}
+// One column of the column pass: the row-pass outputs of one column in, the BIASED coefficients out[u] of that column
+// (source/image_processing.c:253-305).
+M1_HD void fdct_col(int x0, int x1, int x2, int x3, int x4, int x5, int x6, int x7, int (&out)[8])
+{
+    const int r2 = 181;
+    Fdct8 o = fdct_core(x0, x1, x2, x3, x4, x5, x6, x7);
+    const int t4 = o.p3 + o.p1;
+    out[0] = (o.t0 + (16 + (M1_COEF_BIAS << 3))) >> 3;
+    out[4] = (o.t1 + (16 + (M1_COEF_BIAS << 3))) >> 3;
+    out[2] = (o.t2 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
+    out[6] = (o.t3 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
+    out[7] = (t4 - o.t5 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
+    out[1] = (t4 + o.t5 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
+    out[3] = ((o.t6 >> 8) * r2 + (8192 + (M1_COEF_BIAS << 12))) >> 12;
+    out[5] = ((o.t7 >> 8) * r2 + (8192 + (M1_COEF_BIAS << 12))) >> 12;
+}
+M1_HD void fdct8x8(int (&v)[64])
+{
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        Fdct8 o = fdct_core(v[i * 8 + 0], v[i * 8 + 1], v[i * 8 + 2], v[i * 8 + 3],
-                            v[i * 8 + 4], v[i * 8 + 5], v[i * 8 + 6], v[i * 8 + 7]);
-        v[i * 8 + 0] = o.t0;
-        v[i * 8 + 4] = o.t1;
-        v[i * 8 + 2] = o.t2 >> 10;
-        v[i * 8 + 6] = o.t3 >> 10;
-        v[i * 8 + 7] = m1_addsub3(o.p3, o.p1, o.t5) >> 10;
-        v[i * 8 + 1] = m1_add3(o.p3, o.p1, o.t5) >> 10;
-        v[i * 8 + 3] = (o.t6 * r2) >> 17;
-        v[i * 8 + 5] = (o.t7 * r2) >> 17;
+        int o[8];
+        fdct_row(v[i * 8 + 0], v[i * 8 + 1], v[i * 8 + 2], v[i * 8 + 3], v[i * 8 + 4], v[i * 8 + 5], v[i * 8 + 6], v[i * 8 + 7], o);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[i * 8 + k] = o[k];
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-        Fdct8 o = fdct_core(v[0 * 8 + j], v[1 * 8 + j], v[2 * 8 + j], v[3 * 8 + j],
-                            v[4 * 8 + j], v[5 * 8 + j], v[6 * 8 + j], v[7 * 8 + j]);
-        const int t4 = o.p3 + o.p1;
-        v[0 * 8 + j] = (o.t0 + (16 + (M1_COEF_BIAS << 3))) >> 3;
-        v[4 * 8 + j] = (o.t1 + (16 + (M1_COEF_BIAS << 3))) >> 3;
-        v[2 * 8 + j] = (o.t2 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
-        v[6 * 8 + j] = (o.t3 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
-        v[7 * 8 + j] = (t4 - o.t5 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
-        v[1 * 8 + j] = (t4 + o.t5 + (16384 + (M1_COEF_BIAS << 13))) >> 13;
-        v[3 * 8 + j] = ((o.t6 >> 8) * r2 + (8192 + (M1_COEF_BIAS << 12))) >> 12;
-        v[5 * 8 + j] = ((o.t7 >> 8) * r2 + (8192 + (M1_COEF_BIAS << 12))) >> 12;
+        int o[8];
+        fdct_col(v[0 * 8 + j], v[1 * 8 + j], v[2 * 8 + j], v[3 * 8 + j], v[4 * 8 + j], v[5 * 8 + j], v[6 * 8 + j], v[7 * 8 + j], o);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u * 8 + j] = o[u];
     }
 }
 

@@ -309,7 +309,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     uint32_t *win = (uint32_t *)(planes + 6 * C * 64);           // [M1_WIN_WORDS + 4]
     M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS + 4);         // 16-byte aligned
     int *wtot = (int *)(tb + 1);                                 // [48]: [0..3] bits per warp, [4..7] fix-up queue lengths, [8] pair split,
-                                                                 // [9] blocks queued for the DCT, [16..47] their indices (bytes); 16-byte aligned
+                                                                 // [16..47] per warp: lanes of the blocks that need a DCT (bytes); 16-byte aligned
 
     // Per-CTA prologue, kept short: the coder's tables up to zofs[] in 128-bit pieces (the non-zero
     // keys come from the constant bank), and only the first blockDim.x window words zeroed -- a chunk
@@ -330,7 +330,6 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     __syncwarp();
 #endif
     if (tid < 4 && tid >= (nthr >> 5)) wtot[tid] = 0;           // bit totals of the warps this CTA does not have (the others write theirs)
-    if (tid == 0) wtot[9] = 0;                                  // blocks queued for the DCT (phase 2b)
 
     const uint8_t *fr = rgb + (size_t)frame * g.frame_stride;
 
@@ -446,12 +445,16 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
 
     // ---- phase 2: one thread per 8x8 block, threads in CODING order (t = 6*mb + blk), so the
     // bit offsets are a plain scan over the thread index.  pb = the thread's plane block.
-    //   2a  every block thread reads its block once for min / max / sum.  A block whose samples span at most
-    //       g.flat_range cannot have a non-zero AC level at this quality (m1_flat_range, m1cu_quant.h): its DC
-    //       coefficient is (sum + 16) >> 3 and it is done.  The others are queued.
-    //   2b  the queued blocks are transformed and tested by ALL threads of the CTA, one block per thread (the fourth
-    //       warp, which owns no block, takes its share): the cost follows the number of blocks that need a DCT,
-    //       not the number of warps that contain one.
+    //   2a  every block thread reads its block for min / max / sum.  A block whose samples span at most g.flat_range
+    //       cannot have a non-zero AC level at this quality (m1_flat_range, m1cu_quant.h): its DC coefficient is
+    //       (sum + 16) >> 3 and it is done.
+    //   2b  the blocks that do need a DCT, per warp (no CTA barrier anywhere in this phase):
+    //       - all or nearly all of the warp's blocks (busy content, or no flat range at this quality): one thread per
+    //         block, the whole block in registers, exactly as before;
+    //       - a few of them: EIGHT lanes per block (a row each, then a column each, exchanged through the block's own
+    //         256 bytes), four blocks per round -- cost and latency follow the number of blocks that need a DCT, not
+    //         the mere presence of one in the warp; each owner then reads its coefficients back.
+    //   2c  the owner packs and tests the coefficients and writes the record.
     //   3   every block thread codes its own block from its record and non-zero mask.
     const int mb = tid / 6, blk = tid - mb * 6;             // macroblock in chunk, block 0..5
     const bool active = mb < nmb;
@@ -460,11 +463,10 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     const int lane = tid & 31, warp = tid >> 5;
     unsigned long long nz = 0;
     BitAcc acc{0u, 0u, 0};
-    unsigned char *todo = (unsigned char *)(wtot + 16);      // [128] coding-order indices of the blocks that need a DCT
-    bool queued = active;
-    if (g.flat_range >= 0) {
+    {
+        bool need = active;                                  // this block needs a DCT
         const unsigned amask = __ballot_sync(0xffffffffu, active);
-        if (active) {
+        if (g.flat_range >= 0 && active) {
             const int key4 = (tid & 7) << 2;                 // == blk_key(pb, C): threads are in coding order
             const int *src = planes + pb * 64;
             int mn = 255, mx = 0, sum = 0;
@@ -480,7 +482,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                 if ((i == 1 || i == 3) && __all_sync(amask, mx - mn > g.flat_range)) break;
             }
             if (mx - mn <= g.flat_range) {
-                queued = false;
+                need = false;
                 // source/image_processing.c:296: dct[0][0] = (x6 + 16) >> 3, x6 = sum of the eight row sums
                 const int dcb = (sum + (16 + (M1_COEF_BIAS << 3))) >> 3;
                 const int m0 = 0x7800 - (int)(nk.ka[0] & 0xffffu), c = dcb - M1_COEF_BIAS;
@@ -493,53 +495,88 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                 rec[rec_index(pb, 0, tid & 7)] = (short)dcb;
             }
         }
-    }
-    {   // queue: warp-aggregated slot allocation
-        const unsigned qmask = __ballot_sync(0xffffffffu, queued);
-        if (qmask) {
-            int base = 0;
-            const int leader = __ffs(qmask) - 1;
-            if (lane == leader) base = atomicAdd(wtot + 9, __popc(qmask));
-            base = __shfl_sync(0xffffffffu, base, leader);
-            if (queued) todo[base + __popc(qmask & ((1u << lane) - 1u))] = (unsigned char)tid;
-        }
-    }
-    __syncthreads();
-    {
-        const int n_todo = wtot[9];
-#pragma unroll 1
-        for (int i = tid; i < n_todo; i += nthr) {
-            const int t = todo[i], m2 = t / 6, b2 = t - m2 * 6;
-            const int pb2 = b2 < 4 ? (b2 >> 1) * 2 * C + 2 * m2 + (b2 & 1) : b2 * C + m2;
+        const unsigned nmask = __ballot_sync(0xffffffffu, need);
+        const int n_need = __popc(nmask);
+        if (nmask) {                                          // warp-uniform
             int v[64];
-            {
-                const int key4 = (t & 7) << 2;
-                const int *src = planes + pb2 * 64;
+            if (nmask == amask || n_need > 24) {
+                // one thread per block (seven rounds of the eight-lane form would cost as much)
+                if (need) {
+                    const int key4 = (tid & 7) << 2;
+                    const int *src = planes + pb * 64;
 #pragma unroll
-                for (int k = 0; k < 8; ++k) {
-                    const int o = ((k << 2) ^ key4);
-                    const int4 a = *(const int4 *)(src + o);
-                    const int4 b = *(const int4 *)(src + o + 32);
-                    v[4 * k] = a.x; v[4 * k + 1] = a.y; v[4 * k + 2] = a.z; v[4 * k + 3] = a.w;
-                    v[32 + 4 * k] = b.x; v[32 + 4 * k + 1] = b.y; v[32 + 4 * k + 2] = b.z; v[32 + 4 * k + 3] = b.w;
+                    for (int i = 0; i < 8; ++i) {
+                        const int o = ((i << 2) ^ key4);
+                        const int4 a = *(const int4 *)(src + o);
+                        const int4 b = *(const int4 *)(src + o + 32);
+                        v[4 * i] = a.x; v[4 * i + 1] = a.y; v[4 * i + 2] = a.z; v[4 * i + 3] = a.w;
+                        v[32 + 4 * i] = b.x; v[32 + 4 * i + 1] = b.y; v[32 + 4 * i + 2] = b.z; v[32 + 4 * i + 3] = b.w;
+                    }
+                    fdct8x8(v);
+                }
+            } else {
+                // eight lanes per block.  wlist[k] = lane of the warp's k-th block that needs a DCT.  Scratch = the block's
+                // own 64 words: T[k][r] (row-pass output k of row r) at word ((k ^ s) * 8 + r), s = slot 0..3 of the round
+                // (its four blocks then hit four different bank groups); then the coefficients C[u][j] at
+                // ((u ^ (owner lane & 7)) * 8 + j), which the owner reads back row by row.
+                unsigned char *wlist = (unsigned char *)(wtot + 16) + 32 * warp;
+                if (need) wlist[__popc(nmask & ((1u << lane) - 1u))] = (unsigned char)lane;
+                __syncwarp();
+#pragma unroll 1
+                for (int base = 0; base < n_need; base += 4) {
+                    const int s = lane >> 3, r = lane & 7, q = base + s;
+                    const bool valid = q < n_need;
+                    const int owner = valid ? wlist[q] : 0, t = warp * 32 + owner, m2 = t / 6, b2 = t - m2 * 6;
+                    int *blkw = planes + (b2 < 4 ? (b2 >> 1) * 2 * C + 2 * m2 + (b2 & 1) : b2 * C + m2) * 64;
+                    int x[8], o[8];
+                    if (valid) {
+                        const int key = t & 7, i0 = 2 * r;    // row r = chunks 2r, 2r + 1
+                        const int4 a = *(const int4 *)(blkw + (((i0 & 8) | ((i0 & 7) ^ key)) << 2));
+                        const int4 b = *(const int4 *)(blkw + ((((i0 + 1) & 8) | (((i0 + 1) & 7) ^ key)) << 2));
+                        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                    }
+                    __syncwarp();                             // every row is in registers before T overwrites the samples
+                    if (valid) {
+                        fdct_row(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], o);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) blkw[((k ^ s) << 3) + r] = o[k];
+                    }
+                    __syncwarp();
+                    if (valid) {
+                        const int4 a = *(const int4 *)(blkw + ((r ^ s) << 3)), b = *(const int4 *)(blkw + ((r ^ s) << 3) + 4);
+                        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+                    }
+                    __syncwarp();                             // every column is in registers before C overwrites T
+                    if (valid) {
+                        fdct_col(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], o);
+#pragma unroll
+                        for (int u = 0; u < 8; ++u) blkw[((u ^ (owner & 7)) << 3) + r] = o[u];
+                    }
+                }
+                __syncwarp();
+                if (need) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int *rowp = planes + pb * 64 + ((u ^ (lane & 7)) << 3);
+                        const int4 a = *(const int4 *)rowp, b = *(const int4 *)(rowp + 4);
+                        v[8 * u] = a.x; v[8 * u + 1] = a.y; v[8 * u + 2] = a.z; v[8 * u + 3] = a.w;
+                        v[8 * u + 4] = b.x; v[8 * u + 5] = b.y; v[8 * u + 6] = b.z; v[8 * u + 7] = b.w;
+                    }
                 }
             }
-            fdct8x8(v);
-            // packed coefficient pairs + the zigzag-order non-zero mask (m1cu_block.cuh)
-            uint32_t pk[32];
-            const unsigned long long nz2 = pack_and_flag(v, pk, nk);
-            // the block's samples are in registers now: the first half of its 256 bytes of plane becomes the record,
-            // the first eight bytes of the second half carry the mask to the block's own thread
+            if (need) {
+                // packed coefficient pairs + the zigzag-order non-zero mask (m1cu_block.cuh)
+                uint32_t pk[32];
+                nz = pack_and_flag(v, pk, nk);
+                // the block's coefficients are in registers now: the first half of its 256 bytes of plane becomes the record
 #pragma unroll
-            for (int gI = 0; gI < 8; ++gI)
-                *(uint4 *)(rec + pb2 * 128 + (((gI ^ t) & 7) << 3)) =
-                    make_uint4(pk[4 * gI], pk[4 * gI + 1], pk[4 * gI + 2], pk[4 * gI + 3]);
-            *(unsigned long long *)(planes + pb2 * 64 + 32) = nz2;
+                for (int gI = 0; gI < 8; ++gI)
+                    *(uint4 *)(rec + pb * 128 + (((gI ^ tid) & 7) << 3)) =
+                        make_uint4(pk[4 * gI], pk[4 * gI + 1], pk[4 * gI + 2], pk[4 * gI + 3]);
+            }
         }
     }
-    __syncthreads();
     if (active) {
-        if (queued) nz = *(const unsigned long long *)(planes + pb * 64 + 32);
         // ---- phase 3: code the block into registers ------------------------------------------
         if (blk == 0) { acc.lo = 3u; acc.n = 2; }           // address increment '1' + macroblock_type '1'
         if (code_block(acc, rec, pb, nz, is_luma, tb, tid & 7)) atomicOr(err, M1_ERRBIT_LEVEL);

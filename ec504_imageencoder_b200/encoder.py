@@ -84,6 +84,7 @@ class M1Encoder:
             raise M1Error(rc, (self.lib.m1cu_last_error(None) or b"").decode())
         self._h = h
         self.macroblocks = self.lib.m1cu_macroblocks_per_frame(h)
+        self.flat_range = self.lib.m1cu_flat_range(h)        # blocks spanning at most this skip the DCT (-1: none)
         self.frame_bytes_in = self.lib.m1cu_frame_bytes_in(h)
         self.payload_bound = self.lib.m1cu_payload_bound(h)
         self._stream = None
