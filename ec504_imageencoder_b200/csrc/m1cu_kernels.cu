@@ -266,7 +266,9 @@ __device__ __noinline__ void color_half_tile_generic(const uint8_t *__restrict__
 // kLoad: 3 / 4 = FULL mode with aligned 3- / 4-byte pixels (fast half-tiles), 0 = FULL mode generic
 // loads only, -1 = REF_COMPAT.  One instantiation per input format keeps each kernel's code small.
 #ifndef M1_ENC_MIN_CTAS
-#define M1_ENC_MIN_CTAS 7   // 72 registers: 7 CTAs/SM measured best (6: -1.3 %, 8: -4 %, spills)
+#define M1_ENC_MIN_CTAS 8   // 64 registers, 8 CTAs/SM (= what the shared memory allows).  The spills land in the one-thread-per-block
+                            // DCT, which most warps no longer run: 8 beats 7 (72 registers) by 1.3 % on the default content and by 0.5 %
+                            // on noise (profiles/r2_cta8_ab.txt); before the flat-block shortcut 8 lost 4 % to 7
 #endif
 template <int kLoad, bool kLevels>
 __global__ void __launch_bounds__(128, M1_ENC_MIN_CTAS)
