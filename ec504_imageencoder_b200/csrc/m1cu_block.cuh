@@ -311,6 +311,10 @@ M1_HD int code_block(Sink &s, const short *rec, int tid, unsigned long long nz,
     } else {
         if (is_luma) s.put(4u, 3); else s.put(0u, 2);
     }
+    if ((nz >> 1) == 0ull) {                                  // no AC level at all (every flat block): end of block
+        s.put(2u, 2);
+        return 0;
+    }
     // coding stops at the first non-zero whose predecessor position is also non-zero
     const unsigned long long adj = nz & (nz << 1);
     if (adj) m &= (adj & (0ull - adj)) - 1ull;

@@ -472,16 +472,20 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
             const int key4 = (tid & 7) << 2;                 // == blk_key(pb, C): threads are in coding order
             const int *src = planes + pb * 64;
             int mn = 255, mx = 0, sum = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
+            // two rows per step (rows i and i + 4 of the block); straight-line code, so the eight addresses are immediates
+            auto rows = [&](int i) {
                 const int o = ((i << 2) ^ key4);
                 const int4 a = *(const int4 *)(src + o);
                 const int4 b = *(const int4 *)(src + o + 32);
                 mn = __vimin3_s32(mn, a.x, a.y); mn = __vimin3_s32(mn, a.z, a.w); mn = __vimin3_s32(mn, b.x, b.y); mn = __vimin3_s32(mn, b.z, b.w);
                 mx = __vimax3_s32(mx, a.x, a.y); mx = __vimax3_s32(mx, a.z, a.w); mx = __vimax3_s32(mx, b.x, b.y); mx = __vimax3_s32(mx, b.z, b.w);
                 sum = m1_add3(sum, a.x, a.y); sum = m1_add3(sum, a.z, a.w); sum = m1_add3(sum, b.x, b.y); sum = m1_add3(sum, b.z, b.w);
-                // busy content: stop reading as soon as no block of this warp can pass any more
-                if ((i == 1 || i == 3) && __all_sync(amask, mx - mn > g.flat_range)) break;
+            };
+            // busy content: stop reading as soon as no block of this warp can pass any more
+            rows(0); rows(1);
+            if (!__all_sync(amask, mx - mn > g.flat_range)) {
+                rows(2); rows(3);
+                if (!__all_sync(amask, mx - mn > g.flat_range)) { rows(4); rows(5); rows(6); rows(7); }
             }
             if (mx - mn <= g.flat_range) {
                 need = false;
