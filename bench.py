@@ -602,8 +602,9 @@ def run_ours(args):
                          "algorithmic_bytes_per_frame": head["alg_bytes_per_frame"], "frames_per_launch": head["frames_per_launch"],
                          "launch_ms": head["launch_ms"], "whole_step_frac": head["whole_step_frac"],
                          "note": ("the dominant kernel is instruction-issue bound, not HBM bound: the reference's exact double-precision "
-                                  "colour chain + int32 DCT + VLC cost 59 issue slots per pixel, issued at 0.77 per cycle and "
-                                  "sub-partition (two-cycle FP64 / ALU / IMAD instructions), DRAM at 17 % of peak; an integer colour path, "
+                                  "colour chain + int32 DCT + VLC cost 59 issue slots per pixel where every block needs its DCT and about 48 "
+                                  "on the default content (flat blocks get their DC only, see flat_blocks), issued at 0.71 - 0.77 per cycle and "
+                                  "sub-partition (two-cycle FP64 / ALU / IMAD instructions), DRAM at 18 % of peak; an integer colour path, "
                                   "a mixed one, a barrier-free warp-per-chunk kernel and a queue-fed persistent form were built, are "
                                   "bit-exact and measured slower (DESIGN.md section 7, profiles/r2_*)"),
                          "kernel_ms_per_step": head["kernel_ms_per_step"]},
