@@ -503,7 +503,7 @@ class Bench:
 
 
 def run_ours(args):
-    from ec504_imageencoder_b200 import SYNTH_NATURAL, SYNTH_NOISE, SYNTH_GREY, SYNTH_RG_EQUAL
+    from ec504_imageencoder_b200 import SYNTH_NATURAL, SYNTH_NOISE, SYNTH_GREY, SYNTH_RG_EQUAL, SYNTH_SCATTERED
     b = Bench(args)
     world, rank = b.world, b.rank
     steps, warmup = args.steps, max(args.warmup, 3)
@@ -533,6 +533,8 @@ def run_ours(args):
                      ("configs[4] 8K, one GPU's share of 120 frames over 8 (15 frames)", 7680, 4320, 15, 12, SYNTH_NATURAL),
                      ("1080p x 300 noise, quality 12", W, H, 300, 12, SYNTH_NOISE),
                      ("1080p x 300 noise, quality 50 (VLC stress)", W, H, 300, 50, SYNTH_NOISE),
+                     ("1080p x 300 scattered (a quarter of the 8x8 pixel tiles are noise: busy and flat blocks in every warp), quality 12",
+                      W, H, 300, 12, SYNTH_SCATTERED),
                      ("1080p x 300 grey (every pixel an exact-quotient case of the colour arithmetic), quality 12", W, H, 300, 12, SYNTH_GREY),
                      ("1080p x 300 r == g (every pixel an exact-quotient case of Cb), quality 12", W, H, 300, 12, SYNTH_RG_EQUAL)]
             for name, w, h, nfr, q, kind in cases:

@@ -265,6 +265,10 @@ __device__ __noinline__ void color_half_tile_generic(const uint8_t *__restrict__
 // -------------------------------------------------------------------------------------------
 // kLoad: 3 / 4 = FULL mode with aligned 3- / 4-byte pixels (fast half-tiles), 0 = FULL mode generic
 // loads only, -1 = REF_COMPAT.  One instantiation per input format keeps each kernel's code small.
+#ifndef M1_LANES8_MAX
+#define M1_LANES8_MAX 24    // a warp with at most this many blocks that need a DCT (and at least one that does not) uses eight lanes per block
+                            // (4 / 8 / 12 / 16 / 24 measured on scattered content: 1.544 / 1.569 / 1.593 / 1.521 / 1.518 ms, profiles/r2_variants_ab.txt)
+#endif
 #ifndef M1_ENC_MIN_CTAS
 #define M1_ENC_MIN_CTAS 8   // 64 registers, 8 CTAs/SM (= what the shared memory allows).  The spills land in the one-thread-per-block
                             // DCT, which most warps no longer run: 8 beats 7 (72 registers) by 1.3 % on the default content and by 0.5 %
@@ -277,7 +281,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                 uint32_t *__restrict__ staging, uint32_t *__restrict__ chunk_bits,
                 short *__restrict__ levels, int *__restrict__ err)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    extern __shared__ __align__(256) unsigned char smem[];   // 256: the eight-lane DCT places words by XOR on the byte address
     const int tid = threadIdx.x, nthr = blockDim.x;
     const int chunk = blockIdx.x, slice = blockIdx.y, frame = blockIdx.z;
     const int C = g.chunk_mbs;
@@ -310,8 +314,8 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     short *rec = (short *)smem;                                  // aliases planes (see layout note)
     uint32_t *win = (uint32_t *)(planes + 6 * C * 64);           // [M1_WIN_WORDS + 4]
     M1Tables *tb = (M1Tables *)(win + M1_WIN_WORDS + 4);         // 16-byte aligned
-    int *wtot = (int *)(tb + 1);                                 // [48]: [0..3] bits per warp, [4..7] fix-up queue lengths, [8] pair split,
-                                                                 // [16..47] per warp: lanes of the blocks that need a DCT (bytes); 16-byte aligned
+    int *wtot = (int *)(tb + 1);                                 // [64]: [0..3] bits per warp, [4..7] fix-up queue lengths, [8] pair split,
+                                                                 // [16..63] per warp: (plane block, lane) of the blocks that need a DCT; 16-byte aligned
 
     // Per-CTA prologue, kept short: the coder's tables up to zofs[] in 128-bit pieces (the non-zero
     // keys come from the constant bank), and only the first blockDim.x window words zeroed -- a chunk
@@ -505,8 +509,8 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
         const int n_need = __popc(nmask);
         if (nmask) {                                          // warp-uniform
             int v[64];
-            if (nmask == amask || n_need > 24) {
-                // one thread per block (seven rounds of the eight-lane form would cost as much)
+            if (nmask == amask || n_need > M1_LANES8_MAX) {
+                // one thread per block (six rounds of the eight-lane form would cost as much)
                 if (need) {
                     const int key4 = (tid & 7) << 2;
                     const int *src = planes + pb * 64;
@@ -525,18 +529,21 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                 // own 64 words: T[k][r] (row-pass output k of row r) at word ((k ^ s) * 8 + r), s = slot 0..3 of the round
                 // (its four blocks then hit four different bank groups); then the coefficients C[u][j] at
                 // ((u ^ (owner lane & 7)) * 8 + j), which the owner reads back row by row.
-                unsigned char *wlist = (unsigned char *)(wtot + 16) + 32 * warp;
-                if (need) wlist[__popc(nmask & ((1u << lane) - 1u))] = (unsigned char)lane;
+                unsigned short *wlist = (unsigned short *)(wtot + 16) + 24 * warp;   // [<= M1_LANES8_MAX] (plane block << 8) | lane
+                if (need) wlist[__popc(nmask & ((1u << lane) - 1u))] = (unsigned short)((pb << 8) | lane);
                 __syncwarp();
 #pragma unroll 1
                 for (int base = 0; base < n_need; base += 4) {
                     const int s = lane >> 3, r = lane & 7, q = base + s;
                     const bool valid = q < n_need;
-                    const int owner = valid ? wlist[q] : 0, t = warp * 32 + owner, m2 = t / 6, b2 = t - m2 * 6;
-                    int *blkw = planes + (b2 < 4 ? (b2 >> 1) * 2 * C + 2 * m2 + (b2 & 1) : b2 * C + m2) * 64;
+                    const int ent = valid ? wlist[q] : 0, owner = ent & 31;
+                    int *blkw = planes + (ent >> 8) * 64;
                     int x[8], o[8];
+                    // shared-space byte address of word r of the block; the block is 256-byte aligned, so a word index
+                    // ((k ^ s) << 3) + r is the XOR of (k << 5) into (that address ^ (s << 5)): one LOP3 per store
+                    const unsigned sb = (unsigned)__cvta_generic_to_shared(blkw) + 4u * r;
                     if (valid) {
-                        const int key = t & 7, i0 = 2 * r;    // row r = chunks 2r, 2r + 1
+                        const int key = owner & 7, i0 = 2 * r;    // (the owner's coding index & 7; warps start at multiples of 8) row r = chunks 2r, 2r + 1
                         const int4 a = *(const int4 *)(blkw + (((i0 & 8) | ((i0 & 7) ^ key)) << 2));
                         const int4 b = *(const int4 *)(blkw + ((((i0 + 1) & 8) | (((i0 + 1) & 7) ^ key)) << 2));
                         x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
@@ -544,8 +551,9 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                     __syncwarp();                             // every row is in registers before T overwrites the samples
                     if (valid) {
                         fdct_row(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], o);
+                        const unsigned aT = sb ^ ((unsigned)s << 5);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) blkw[((k ^ s) << 3) + r] = o[k];
+                        for (int k = 0; k < 8; ++k) asm volatile("st.shared.b32 [%0], %1;" :: "r"(aT ^ (unsigned)(k << 5)), "r"(o[k]) : "memory");
                     }
                     __syncwarp();
                     if (valid) {
@@ -555,16 +563,20 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
                     __syncwarp();                             // every column is in registers before C overwrites T
                     if (valid) {
                         fdct_col(x[0], x[1], x[2], x[3], x[4], x[5], x[6], x[7], o);
+                        const unsigned aC = sb ^ ((unsigned)(owner & 7) << 5);
 #pragma unroll
-                        for (int u = 0; u < 8; ++u) blkw[((u ^ (owner & 7)) << 3) + r] = o[u];
+                        for (int u = 0; u < 8; ++u) asm volatile("st.shared.b32 [%0], %1;" :: "r"(aC ^ (unsigned)(u << 5)), "r"(o[u]) : "memory");
                     }
                 }
                 __syncwarp();
                 if (need) {
+                    // row u of the coefficients sits at word (u ^ (lane & 7)) << 3 of the block: XOR on the byte address again
+                    const unsigned rb = ((unsigned)__cvta_generic_to_shared(planes + pb * 64)) ^ ((unsigned)(lane & 7) << 5);
 #pragma unroll
                     for (int u = 0; u < 8; ++u) {
-                        const int *rowp = planes + pb * 64 + ((u ^ (lane & 7)) << 3);
-                        const int4 a = *(const int4 *)rowp, b = *(const int4 *)(rowp + 4);
+                        int4 a, b;
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w) : "r"(rb ^ (unsigned)(u << 5)) : "memory");
+                        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4+16];" : "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "r"(rb ^ (unsigned)(u << 5)) : "memory");
                         v[8 * u] = a.x; v[8 * u + 1] = a.y; v[8 * u + 2] = a.z; v[8 * u + 3] = a.w;
                         v[8 * u + 4] = b.x; v[8 * u + 5] = b.y; v[8 * u + 6] = b.z; v[8 * u + 7] = b.w;
                     }
@@ -959,7 +971,10 @@ __global__ void k_synth_rgb(uint32_t seed, long first_frame, int n_frames, int W
         const uint32_t fkey = mix32(seed * 0x85ebca6bu + f * 0x9e3779b9u + 0x165667b1u);
         const uint32_t n = mix32(fkey ^ (y * (uint32_t)W + x));
         uint8_t *o = rgb + i * 3;
-        if (kind == 1) {
+        bool noisy = kind == 1;
+        if (kind == 4)                                              // scattered: a quarter of the 8x8 pixel tiles are noise
+            noisy = (mix32(fkey ^ (0x51ed270bu + ((y >> 3) * 0x9e3779b1u) + (x >> 3))) & 3u) == 0u;
+        if (noisy) {
             o[0] = (uint8_t)n; o[1] = (uint8_t)(n >> 8); o[2] = (uint8_t)(n >> 16);
         } else {
             o[0] = (uint8_t)((255u * x / (uint32_t)W + (n & 15u) + f) & 255u);
@@ -982,7 +997,7 @@ size_t m1k_encode_smem_bytes(const M1Geom &g, int threads)
 #else
     const size_t pad = 0;
 #endif
-    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 4) * 4 + sizeof(M1Tables) + 48 * sizeof(int) + 16 + pad;
+    return (size_t)6 * g.chunk_mbs * 256 + (size_t)(M1_WIN_WORDS + 4) * 4 + sizeof(M1Tables) + 64 * sizeof(int) + 16 + pad;
 }
 
 int m1k_encode_threads(const M1Geom &g) { return (8 * g.chunk_mbs + 31) & ~31; }   // one colour tile per thread; 6C of them own a block

@@ -20,7 +20,7 @@ from . import _native
 
 MODE_FULL = 0        # raster macroblocks, 4:2:0 chroma (BASELINE configs)
 MODE_REF_COMPAT = 1  # literal traversal of include/encoder.h:238-443 (drop-in byte parity)
-SYNTH_NATURAL, SYNTH_NOISE, SYNTH_GREY, SYNTH_RG_EQUAL = 0, 1, 2, 3
+SYNTH_NATURAL, SYNTH_NOISE, SYNTH_GREY, SYNTH_RG_EQUAL, SYNTH_SCATTERED = 0, 1, 2, 3, 4
 DEFAULT_QUALITY = 12  # reference main.c:16
 
 _ERRORS = {-1: "bad argument", -2: "CUDA failure / no device", -3: "output capacity",

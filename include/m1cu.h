@@ -61,7 +61,8 @@ enum m1cu_status {
 
 enum m1cu_synth_kind { M1CU_SYNTH_NATURAL = 0, M1CU_SYNTH_NOISE = 1,
                        M1CU_SYNTH_GREY = 2,      /* natural's R channel in all three: every pixel is an exact-quotient case */
-                       M1CU_SYNTH_RG_EQUAL = 3   /* natural with G := R                                                   */ };
+                       M1CU_SYNTH_RG_EQUAL = 3,  /* natural with G := R                                                   */
+                       M1CU_SYNTH_SCATTERED = 4  /* natural with a quarter of its 8x8 pixel tiles replaced by noise      */ };
 
 typedef struct m1cu_ctx m1cu_ctx;
 

@@ -531,7 +531,12 @@ void m1o_synth_rgb(uint32_t seed, long frame_index, int W, int H, int kind, uint
         for (int x = 0; x < W; ++x) {
             uint32_t n = mix32(fkey ^ ((uint32_t)y * (uint32_t)W + (uint32_t)x));
             uint8_t *p = rgb + ((long)y * W + x) * 3;
-            if (kind == M1O_SYNTH_NOISE) {
+            /* M1O_SYNTH_SCATTERED: the natural picture with a quarter of its 8x8 pixel tiles (chosen by a hash of the tile's
+             * position and the frame) replaced by noise -- busy and flat blocks side by side inside every warp of the encoder */
+            int noisy = kind == M1O_SYNTH_NOISE;
+            if (kind == M1O_SYNTH_SCATTERED)
+                noisy = (mix32(fkey ^ (0x51ed270bu + ((uint32_t)(y >> 3) * 0x9e3779b1u) + (uint32_t)(x >> 3))) & 3u) == 0u;
+            if (noisy) {
                 p[0] = (uint8_t)n; p[1] = (uint8_t)(n >> 8); p[2] = (uint8_t)(n >> 16);
             } else {
                 p[0] = (uint8_t)((255u * (uint32_t)x / (uint32_t)W + (n & 15u) + f) & 255u);

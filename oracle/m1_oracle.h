@@ -23,7 +23,7 @@ extern "C" {
 #endif
 
 enum { M1O_MODE_FULL = 0, M1O_MODE_REF_COMPAT = 1 };
-enum { M1O_SYNTH_NATURAL = 0, M1O_SYNTH_NOISE = 1, M1O_SYNTH_GREY = 2, M1O_SYNTH_RG_EQUAL = 3 };
+enum { M1O_SYNTH_NATURAL = 0, M1O_SYNTH_NOISE = 1, M1O_SYNTH_GREY = 2, M1O_SYNTH_RG_EQUAL = 3, M1O_SYNTH_SCATTERED = 4 };
 
 /* source/image_processing.c:314-343 (scale_quantization_matrix); out is row-major [i*8+j]. */
 void m1o_qmatrix(int quality_factor, int32_t out[64]);

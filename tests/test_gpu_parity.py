@@ -10,7 +10,7 @@ torch = pytest.importorskip("torch")
 pytestmark = pytest.mark.gpu
 
 import oracle  # noqa: E402
-from oracle import MODE_FULL, MODE_REF_COMPAT, SYNTH_NATURAL, SYNTH_NOISE, SYNTH_GREY, SYNTH_RG_EQUAL  # noqa: E402
+from oracle import MODE_FULL, MODE_REF_COMPAT, SYNTH_NATURAL, SYNTH_NOISE, SYNTH_GREY, SYNTH_RG_EQUAL, SYNTH_SCATTERED  # noqa: E402
 
 
 @pytest.fixture(scope="module")
@@ -140,6 +140,14 @@ def test_exact_quotient_worst_cases(m1, port, kind, W, H, q):
     land one ulp below an integer, the worst case for any shortcut in the colour
     arithmetic (on the integer-colour build every 2x2 quad of every chunk is queued for recomputation)."""
     _encode_both(m1, port, W, H, 2, q, kind)
+
+
+@pytest.mark.parametrize("W,H,q,mode", [(352, 240, 12, MODE_FULL), (1920, 1080, 12, MODE_FULL), (1920, 1080, 5, MODE_FULL),
+                                        (640, 368, 20, MODE_FULL), (400, 600, 12, MODE_REF_COMPAT)])
+def test_scattered_busy_tiles(m1, port, W, H, q, mode):
+    """A quarter of the 8x8 pixel tiles are noise, the rest smooth: flat and busy blocks side by side in every warp, so
+    the encoder's three block paths (DC only, eight lanes per busy block, one thread per block) all run inside one chunk."""
+    _encode_both(m1, port, W, H, 2, q, SYNTH_SCATTERED, mode)
 
 
 @pytest.mark.parametrize("channels", [3, 4])
