@@ -79,6 +79,33 @@ def test_flat_block_skip_at_the_boundary(port, quality):
         enc.close()
 
 
+def test_random_geometries_qualities_contents(port):
+    """Sixty random combinations of picture size (aligned and ragged: fast and generic colour loads), quality (1 .. 80: flat
+    ranges from 218 grey levels down to none), content kind (all five generators) and chunk size: levels and bytes against the
+    oracle.  Every block path of the encoder (DC only, eight lanes per block, one thread per block) occurs many times over."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from ec504_imageencoder_b200 import M1Encoder
+    rng = np.random.default_rng(20261019)
+    for case in range(60):
+        W = int(rng.choice([16 * int(rng.integers(1, 26)), int(rng.integers(1, 400))]))
+        H = int(rng.choice([16 * int(rng.integers(1, 14)), int(rng.integers(1, 220))]))
+        q = int(rng.integers(1, 81))
+        kind = int(rng.integers(0, 5))
+        cm = int(rng.choice([0, 0, int(rng.integers(1, 17))]))
+        n = int(rng.integers(1, 4))
+        enc = M1Encoder(W, H, 3, 0, q, max_frames=n, chunk_mbs=cm)
+        rgb = enc.synth_rgb(1000 + case, case, n, kind)
+        res = enc.encode_device(rgb, want_levels=True)
+        pay2 = enc.encode_device(rgb).payloads()
+        pay, host, lev = res.payloads(), rgb.cpu().numpy(), res.levels.cpu().numpy()
+        for f in range(n):
+            rp, rl = port.encode_picture(host[f], q, 0, want_levels=True)
+            assert np.array_equal(lev[f], rl), (case, W, H, q, kind, cm, f)
+            assert pay[f] == rp and pay2[f] == rp, (case, W, H, q, kind, cm, f)
+        enc.close()
+
+
 def test_launch_rounds_overlap(port):
     """A call with more pictures than one launch round holds (batch_frames) runs the layout + stitch of a round on a
     side stream beside the next round's chunk encoder, on two sets of staging buffers: 23 pictures in rounds of 4,
