@@ -237,7 +237,10 @@ int m1cu_create_ex(m1cu_ctx **out, int device, int width, int height, int channe
     m1cu_qmatrix(quality, ctx->qm);
     if (!m1_make_quant(ctx->qm, &ctx->q)) { delete ctx; return fail(nullptr, M1CU_ERR_ARG, "m1cu_create: quantiser constants failed self-check"); }
     // blocks whose samples span at most flat_range have no non-zero AC level at this quality: they skip DCT + test
+    // (a range below 6 grey levels -- quality 40 and up -- is not worth the test: sensor noise alone spans more, and the test
+    // plus the 64-register build cost 3 % where nothing qualifies, profiles/r2_flat_skip_ab.txt)
     g.flat_range = (tuning && tuning->no_flat_skip) ? -1 : m1_flat_range(ctx->qm);
+    if (g.flat_range < 6) g.flat_range = -1;
 
 #define CUC(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = fail(ctx, M1CU_ERR_CUDA, #call, e_); memcpy(g_last_error, ctx->err, sizeof g_last_error); m1cu_destroy(ctx); return rc_; } } while (0)
     CUC(cudaSetDevice(device));

@@ -274,8 +274,10 @@ __device__ __noinline__ void color_half_tile_generic(const uint8_t *__restrict__
                             // DCT, which most warps no longer run: 8 beats 7 (72 registers) by 1.3 % on the default content and by 0.5 %
                             // on noise (profiles/r2_cta8_ab.txt); before the flat-block shortcut 8 lost 4 % to 7
 #endif
-template <int kLoad, bool kLevels>
-__global__ void __launch_bounds__(128, M1_ENC_MIN_CTAS)
+// kFlat: the quality has a flat range (g.flat_range >= 0): 64 registers / 8 CTAs per SM.  Without one every block runs the
+// one-thread DCT, which wants its 72 registers: 7 CTAs per SM as before.
+template <int kLoad, bool kLevels, bool kFlat>
+__global__ void __launch_bounds__(128, kFlat ? M1_ENC_MIN_CTAS : M1_ENC_MIN_CTAS - 1)
 k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKeys nk,
                 const uint8_t *__restrict__ rgb, const M1Tables *__restrict__ gtab,
                 uint32_t *__restrict__ staging, uint32_t *__restrict__ chunk_bits,
@@ -472,7 +474,7 @@ k_encode_chunks(const __grid_constant__ M1Geom g, const __grid_constant__ M1NzKe
     {
         bool need = active;                                  // this block needs a DCT
         const unsigned amask = __ballot_sync(0xffffffffu, active);
-        if (g.flat_range >= 0 && active) {
+        if (kFlat && active) {
             const int key4 = (tid & 7) << 2;                 // == blk_key(pb, C): threads are in coding order
             const int *src = planes + pb * 64;
             int mn = 255, mx = 0, sum = 0;
@@ -1005,12 +1007,19 @@ int m1k_encode_threads(const M1Geom &g) { return (8 * g.chunk_mbs + 31) & ~31; }
 typedef void (*encode_kernel_t)(const M1Geom, const M1NzKeys, const uint8_t *, const M1Tables *, uint32_t *, uint32_t *,
                                 short *, int *);
 
+template <int kLoad>
+static encode_kernel_t pick_encode_kernel_for(bool levels, bool flat)
+{
+    if (flat) return levels ? k_encode_chunks<kLoad, true, true> : k_encode_chunks<kLoad, false, true>;
+    return levels ? k_encode_chunks<kLoad, true, false> : k_encode_chunks<kLoad, false, false>;
+}
 static encode_kernel_t pick_encode_kernel(const M1Geom &g, bool levels)
 {
-    if (g.mode != 0) return levels ? k_encode_chunks<-1, true> : k_encode_chunks<-1, false>;
-    if (g.fast_load == 3) return levels ? k_encode_chunks<3, true> : k_encode_chunks<3, false>;
-    if (g.fast_load == 4) return levels ? k_encode_chunks<4, true> : k_encode_chunks<4, false>;
-    return levels ? k_encode_chunks<0, true> : k_encode_chunks<0, false>;
+    const bool flat = g.flat_range >= 0;
+    if (g.mode != 0) return pick_encode_kernel_for<-1>(levels, flat);
+    if (g.fast_load == 3) return pick_encode_kernel_for<3>(levels, flat);
+    if (g.fast_load == 4) return pick_encode_kernel_for<4>(levels, flat);
+    return pick_encode_kernel_for<0>(levels, flat);
 }
 
 cudaError_t m1k_prepare(const M1Geom &g)

@@ -102,7 +102,8 @@ int  m1cu_synchronize(m1cu_ctx *ctx);
 /* geometry / sizing */
 int    m1cu_macroblocks_per_frame(const m1cu_ctx *ctx);
 int    m1cu_flat_range(const m1cu_ctx *ctx);               /* largest sample span of an 8x8 block that proves every AC level
-                                                              zero at this quality (such blocks skip the DCT); -1: none / off */
+                                                              zero at this quality (such blocks skip the DCT); -1: none, below
+                                                              6 grey levels (not worth the test), or switched off            */
 size_t m1cu_frame_bytes_in(const m1cu_ctx *ctx);           /* width*height*channels             */
 size_t m1cu_payload_bound(const m1cu_ctx *ctx);            /* worst-case payload bytes per frame,
                                                               multiple of 16                    */

@@ -51,7 +51,7 @@ def test_flat_block_skip_at_the_boundary(port, quality):
     if not torch.cuda.is_available():
         pytest.skip("no GPU")
     from ec504_imageencoder_b200 import M1Encoder
-    R = {5: 42, 12: 16, 20: 10, 50: 2, 89: 0}[quality]
+    R = {5: 42, 12: 16, 20: 10, 50: 2, 89: 0}[quality]      # m1_flat_range; the library uses it from 6 up (quality 50, 89: no shortcut)
     W, H, n = 640, 368, 4
     rng = np.random.default_rng(quality)
     frames = np.zeros((n, H, W, 3), np.uint8)

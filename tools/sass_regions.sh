@@ -1,9 +1,9 @@
 #!/bin/sh
-# Static SASS opcode histogram of k_encode_chunks<3,false> between its barriers (no GPU needed).
+# Static SASS opcode histogram of k_encode_chunks<3,false,true> between its barriers (no GPU needed).
 # usage: tools/sass_regions.sh <libm1cu.so> [region: 0 = colour phase, 1 = block phase]
 LIB=${1:-ec504_imageencoder_b200/libm1cu.so}; R=${2:-1}
 F=$(mktemp)
-cuobjdump -sass -fun '_Z15k_encode_chunksILi3ELb0EEv6M1Geom8M1NzKeysPKhPK8M1TablesPjS7_PsPi' "$LIB" > "$F"
+cuobjdump -sass -fun '_Z15k_encode_chunksILi3ELb0ELb1EEv6M1Geom8M1NzKeysPKhPK8M1TablesPjS7_PsPi' "$LIB" > "$F"
 echo "total static instructions: $(grep -c '^\s*/\*[0-9a-f]\{4\}\*/' "$F")"
 if [ "$R" = 0 ]; then A=1; else A=$(grep -n "BAR.SYNC" "$F" | sed -n "${R}p" | cut -d: -f1); fi
 B=$(grep -n "BAR.SYNC" "$F" | sed -n "$((R+1))p" | cut -d: -f1)
