@@ -65,19 +65,25 @@ void dequantization(int quantized_block[8][8], double dct_block[8][8])
         for (int j = 0; j < 8; ++j) dct_block[i][j] = quantized_block[i][j] * Q_MATRIX[i][j];
 }
 
+/* The reference's int arithmetic overflows for large coefficients (undefined behaviour that every gcc build resolves as
+ * two's-complement wrap-around): reproduced with unsigned arithmetic, which wraps by definition. */
+static inline int w_add(int a, int b) { return (int)((unsigned)a + (unsigned)b); }
+static inline int w_sub(int a, int b) { return (int)((unsigned)a - (unsigned)b); }
+static inline int w_mul(int a, int b) { return (int)((unsigned)a * (unsigned)b); }
+
 static void pass8(const int x[8], int o[8])
 {
     /* the same butterfly as fast_DCT (the reference's fast_IDCT reuses the forward stages) */
     enum { c1 = 1004, s1 = 200, c3 = 851, s3 = 569, r2c6 = 554, r2s6 = 1337 };
-    const int s07 = x[0] + x[7], d07 = x[0] - x[7], s16 = x[1] + x[6], d16 = x[1] - x[6];
-    const int s25 = x[2] + x[5], d25 = x[2] - x[5], s34 = x[3] + x[4], d34 = x[3] - x[4];
-    const int ee = s07 + s34, eo = s07 - s34, oe = s16 + s25, oo = s16 - s25;
-    const int ta = c1 * (d16 + d25), tb = c3 * (d07 + d34), tc = r2c6 * (oo + eo);
-    const int y2 = (-s1 - c1) * d25 + ta, y1 = (s1 - c1) * d16 + ta;
-    const int y3 = (-s3 - c3) * d34 + tb, y0 = (s3 - c3) * d07 + tb;
-    o[0] = ee + oe; o[1] = ee - oe;
-    o[2] = (r2s6 - r2c6) * eo + tc; o[3] = (-r2s6 - r2c6) * oo + tc;
-    o[4] = y3 + y1; o[5] = y0 + y2; o[6] = y3 - y1; o[7] = y0 - y2;
+    const int s07 = w_add(x[0], x[7]), d07 = w_sub(x[0], x[7]), s16 = w_add(x[1], x[6]), d16 = w_sub(x[1], x[6]);
+    const int s25 = w_add(x[2], x[5]), d25 = w_sub(x[2], x[5]), s34 = w_add(x[3], x[4]), d34 = w_sub(x[3], x[4]);
+    const int ee = w_add(s07, s34), eo = w_sub(s07, s34), oe = w_add(s16, s25), oo = w_sub(s16, s25);
+    const int ta = w_mul(c1, w_add(d16, d25)), tb = w_mul(c3, w_add(d07, d34)), tc = w_mul(r2c6, w_add(oo, eo));
+    const int y2 = w_add(w_mul(-s1 - c1, d25), ta), y1 = w_add(w_mul(s1 - c1, d16), ta);
+    const int y3 = w_add(w_mul(-s3 - c3, d34), tb), y0 = w_add(w_mul(s3 - c3, d07), tb);
+    o[0] = w_add(ee, oe); o[1] = w_sub(ee, oe);
+    o[2] = w_add(w_mul(r2s6 - r2c6, eo), tc); o[3] = w_add(w_mul(-r2s6 - r2c6, oo), tc);
+    o[4] = w_add(y3, y1); o[5] = w_add(y0, y2); o[6] = w_sub(y3, y1); o[7] = w_sub(y0, y2);
 }
 
 /* :492-601 -- columns then rows through the FORWARD butterfly, then clamps / shifts as the
@@ -90,8 +96,8 @@ void fast_IDCT(const double dct_block[8][8], unsigned char block[8][8])
         for (int k = 0; k < 8; ++k) in[k] = (int)dct_block[k][i];
         pass8(in, o);
         cols[0][i] = o[0]; cols[4][i] = o[1]; cols[2][i] = o[2] >> 10; cols[6][i] = o[3] >> 10;
-        cols[7][i] = (o[4] - o[5]) >> 10; cols[1][i] = (o[4] + o[5]) >> 10;
-        cols[3][i] = (o[6] * r2) >> 17; cols[5][i] = (o[7] * r2) >> 17;
+        cols[7][i] = w_sub(o[4], o[5]) >> 10; cols[1][i] = w_add(o[4], o[5]) >> 10;
+        cols[3][i] = w_mul(o[6], r2) >> 17; cols[5][i] = w_mul(o[7], r2) >> 17;
     }
     for (int i = 0; i < 8; ++i) {
         pass8(cols[i], o);
@@ -99,10 +105,10 @@ void fast_IDCT(const double dct_block[8][8], unsigned char block[8][8])
         block[i][4] = (unsigned char)(o[1] < 0 ? 0 : (o[1] > 255 ? 255 : o[1]));
         block[i][2] = (unsigned char)(o[2] >> 10);
         block[i][6] = (unsigned char)(o[3] >> 10);
-        block[i][7] = (unsigned char)((o[4] - o[5]) >> 10);
-        block[i][1] = (unsigned char)((o[4] + o[5]) >> 10);
-        block[i][3] = (unsigned char)((o[6] * r2) >> 17);
-        block[i][5] = (unsigned char)((o[7] * r2) >> 17);
+        block[i][7] = (unsigned char)(w_sub(o[4], o[5]) >> 10);
+        block[i][1] = (unsigned char)(w_add(o[4], o[5]) >> 10);
+        block[i][3] = (unsigned char)(w_mul(o[6], r2) >> 17);
+        block[i][5] = (unsigned char)(w_mul(o[7], r2) >> 17);
     }
 }
 

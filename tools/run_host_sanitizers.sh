@@ -18,8 +18,17 @@ OUT=profiles/r2_host_sanitizers.txt
 set +e
 LD_PRELOAD="$ASAN:$UBSAN" ASAN_OPTIONS=detect_leaks=0:abort_on_error=1:halt_on_error=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
 M1_HOSTLIB=$PWD/ec504_imageencoder_b200/libencoder_san.so M1_ORACLE_LIB=$PWD/oracle/libm1oracle_san.so M1_SANITIZER_RUN=1 \
-  python -m pytest tests/test_host_library.py tests/test_oracle_golden.py tests/test_oracle_vs_ref.py tests/test_decoder.py -q -m "not gpu" -p no:cacheprovider 2>&1 | tail -25 >> $OUT
+  python -m pytest tests/test_host_library.py tests/test_oracle_golden.py tests/test_oracle_vs_ref.py tests/test_decoder.py -q -s -m "not gpu" -p no:cacheprovider \
+    --deselect tests/test_oracle_vs_ref.py::test_block_bits > $OUT.full 2>&1
 rc=$?
-grep -c "runtime error\|AddressSanitizer" $OUT | sed 's/^/# sanitizer reports in this log: /' >> $OUT
+# deselected: test_block_bits drives the UNMODIFIED reference (oracle/_ref, not instrumented) with extreme blocks, and the reference
+# itself writes past a heap block there (source/bit_vector.c:111 bitvector_concat <- image_processing.c:427 VLC_encode), which
+# ASan's memcpy interceptor reports; that test still runs, uninstrumented, in the normal CPU suite.
+# -s: a sanitizer abort kills the interpreter, and pytest's captured output would die with it (that is how an overflow in
+# fast_IDCT once went unnoticed: the log ended after six dots and still counted zero reports)
+grep -v "^$" $OUT.full | grep -i "runtime error\|AddressSanitizer\|SUMMARY\|passed\|failed\|error" | head -40 >> $OUT
+grep -c "runtime error\|AddressSanitizer" $OUT.full | sed 's/^/# sanitizer reports in this log: /' >> $OUT
+grep -q " passed" $OUT.full || { echo "# pytest did not finish (rc=$rc): see the tail below" >> $OUT; tail -15 $OUT.full >> $OUT; rc=1; }
+rm -f $OUT.full
 cat $OUT
 exit $rc
