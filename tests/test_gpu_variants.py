@@ -79,6 +79,21 @@ def test_flat_block_skip_at_the_boundary(port, quality):
         enc.close()
 
 
+def test_flat_range_is_reported():
+    """m1cu_flat_range: the bound of csrc/m1cu_quant.h per quality (checked against the oracle in tests/test_block_host.py); the
+    library uses it from 6 grey levels up and not at all with no_flat_skip."""
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from ec504_imageencoder_b200 import M1Encoder
+    for q, want in ((1, 218), (5, 42), (12, 16), (20, 10), (30, 6), (40, -1), (50, -1), (89, -1)):
+        enc = M1Encoder(64, 48, 3, 0, q, max_frames=1)
+        assert enc.flat_range == want, (q, enc.flat_range)
+        enc.close()
+    enc = M1Encoder(64, 48, 3, 0, 12, max_frames=1, no_flat_skip=True)
+    assert enc.flat_range == -1
+    enc.close()
+
+
 def test_random_geometries_qualities_contents(port):
     """Sixty random combinations of picture size (aligned and ragged: fast and generic colour loads), quality (1 .. 80: flat
     ranges from 218 grey levels down to none), content kind (all five generators) and chunk size: levels and bytes against the
